@@ -1,0 +1,79 @@
+"""Pin the oracle: bit-exact against outputs of the reference's own layer code
+(tests/golden/layer_*.npz, made by oracle/gen_golden.py from /root/reference) and
+within the reference's nightly tolerance against stock transformers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import opt_ref
+
+LAYER_CASES = ["layer_d64", "layer_d128", "layer_ragged"]
+
+
+def _bf16(a):
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+
+def load_layer_case(golden_dir, name):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    w = {k[2:]: _bf16(z[k]) for k in z.files if k.startswith("w_")}
+    meta = {k: int(z[k]) for k in ("B", "S", "h", "H", "new")}
+    xs = [_bf16(z[f"x{i}"]) for i in range(meta["new"] + 1)]
+    ys = [_bf16(z[f"y{i}"]) for i in range(meta["new"] + 1)]
+    return meta, w, xs, ys, _bf16(z["kcache"]), _bf16(z["vcache"])
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_bit_exact_vs_reference(golden_dir, name):
+    torch.set_num_threads(1)
+    meta, w, xs, ys, kc_ref, vc_ref = load_layer_case(golden_dir, name)
+    B, S, h, H, new = (meta[k] for k in ("B", "S", "h", "H", "new"))
+    kc = torch.zeros(S + new, B, H, h // H, dtype=torch.bfloat16)
+    vc = torch.zeros_like(kc)
+    cur = 0
+    for x, y_ref in zip(xs, ys):
+        y = opt_ref.layer_forward(x, w, H, kc, vc, cur)
+        cur += x.shape[1]
+        assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16)), name
+    assert torch.equal(kc.view(torch.int16), kc_ref.view(torch.int16))
+    assert torch.equal(vc.view(torch.int16), vc_ref.view(torch.int16))
+
+
+def load_hf_case(golden_dir):
+    z = np.load(os.path.join(golden_dir, "model_hf_tiny.npz"))
+    sd = {k[3:]: _bf16(z[k]) for k in z.files if k.startswith("sd:")}
+    model = opt_ref.model_from_hf_state_dict(sd, int(z["H"]))
+    return z, model
+
+
+def test_model_fp32_matches_stock_transformers(golden_dir):
+    z, model = load_hf_case(golden_dir)
+    m32 = opt_ref.model_to(model, dtype=torch.float32)
+    ids = torch.from_numpy(z["input_ids"])
+    logits = []
+    toks = opt_ref.greedy_generate(m32, ids, int(z["new"]), collect_logits=logits)
+    assert np.array_equal(toks.numpy(), z["tokens"])
+    np.testing.assert_allclose(logits[0].numpy(), z["prefill_last_logits"], atol=2e-5)
+
+
+def test_model_bf16_within_reference_nightly_tolerance(golden_dir):
+    # tests/cpu/test_ipex_optimize_transformers_nightly.py:237 uses prec=0.1 for bf16 vs fp32 logits
+    z, model = load_hf_case(golden_dir)
+    ids = torch.from_numpy(z["input_ids"])
+    logits = []
+    opt_ref.greedy_generate(model, ids, 1, collect_logits=logits)
+    assert np.abs(logits[0].numpy() - z["prefill_last_logits"]).max() < 0.1
+
+
+def test_tp_sharding_restatement_sums_to_full(golden_dir):
+    meta, w, xs, ys, _, _ = load_layer_case(golden_dir, "layer_d64")
+    x = xs[0].float()
+    wf = {k: v.float() for k, v in w.items()}
+    full = torch.relu(x @ wf["fc1_w"].t() + wf["fc1_b"]) @ wf["fc2_w"].t()
+    parts = 0
+    for r in range(2):
+        s = opt_ref.shard_layer(wf, meta["H"], r, 2)
+        parts = parts + torch.relu(x @ s["fc1_w"].t() + s["fc1_b"]) @ s["fc2_w"].t()
+    torch.testing.assert_close(parts, full, atol=1e-4, rtol=1e-4)
