@@ -1,0 +1,622 @@
+// out[M,N] = epilogue(A[M,K] . W[N,K]^T), bf16 in / fp32 accumulate, for sm_100a.
+//
+// Replaces the reference's cuBLAS + ATen elementwise chains:
+//   gpu_linear_compute*, gpu_linear_relu_compute*  (decoder.py:79-105)
+//   the q/k/v projections, Q scaling and KV-cache writes (attentions.py:376-418,456-491)
+//   the residual adds (decoder.py:229,310)
+//
+// Design (B200-first, not a translation of anything in the reference -- it has no GPU kernels):
+//   * one persistent CTA per SM, 256 threads, warp-specialised:
+//       warp 0  TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, mbarrier complete_tx)
+//       warp 1  MMA issuer     (one elected lane issues tcgen05.mma.cta_group::1.kind::f16)
+//       warp 2  TMEM allocator
+//       warps 4-7 epilogue     (tcgen05.ld -> regs -> smem staging -> coalesced 16-byte global I/O)
+//   * accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
+//     overlaps the main loop of tile i+1.
+//   * both operands are K-major ([rows, K] row-major), so `x . W^T` needs no transpose:
+//     W[N,K] is already the K-major "B" operand.
+//   * two modes.  NORMAL (M > 128, prefill, tensor-bound): activations are the UMMA "A"
+//     operand (128 rows per tile), W the "B" operand (BN = 128/256 rows).  SWAP (M <= 128,
+//     decode, HBM-bound on W): W is the "A" operand so that its rows fill UMMA-M = 128, the
+//     few tokens are UMMA-N (16..128); K can be split across CTAs so that every SM streams
+//     weights; partial sums meet in an fp32 workspace and the last CTA to arrive reduces them
+//     in a FIXED order (deterministic) and applies the epilogue.
+//   * epilogue rounding points mirror the reference's eager ops exactly:
+//       r1 = bf16(acc); r2 = bf16(r1 + bias); then relu | bf16(residual + r2) | bf16(r2*scale).
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int TILE_A = 128;   // rows of the UMMA "A" operand per tile (UMMA M)
+constexpr int NUM_THREADS = 256;
+constexpr int EPI_WARP0 = 4;
+constexpr int GROUP_M = 16;   // raster group (A tiles per group) for L2 reuse in NORMAL mode
+constexpr int MAX_SPLITK = 8;
+constexpr int COUNTER_BYTES = 16384;
+constexpr int SWAP_LD = TILE_A + 4;   // fp32 staging pitch (floats) in SWAP mode
+
+struct EpiParams {
+  const bf16* bias;
+  const bf16* residual;
+  bf16* out;
+  int M, N;
+  int mode;
+  // LIA_EPI_QKV
+  bf16* q_out;
+  bf16* k_cache;
+  bf16* v_cache;
+  int hq, S, pos0, cache_batch, b0;
+  float q_scale;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, "
+      "[%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (UMMA SmemDescriptor):
+//   [0,14) start>>4 | [16,30) LBO>>4 (=1, unused for swizzled K-major) | [32,46) SBO>>4 (8 rows * 128 B = 1024 B)
+//   [46,48) version = 1 (Blackwell) | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// kind::f16 instruction descriptor: C=f32 (bit 4), A=B=bf16 (bits 7,10), both K-major, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(umma_n >> 3) << 17) | ((uint32_t)(umma_m >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ epilogue on 8 consecutive columns
+// v[] holds r1 = bf16(acc) (as floats).  Rounding points follow SURVEY.md A.2.
+__device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n, float* v) {
+  if (p.bias != nullptr) {
+    float b[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = bf16r(v[i] + b[i]);
+  }
+  if (p.mode == LIA_EPI_BIAS) {
+    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
+  } else if (p.mode == LIA_EPI_BIAS_RELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
+  } else if (p.mode == LIA_EPI_BIAS_RESIDUAL) {
+    float r[8];
+    unpack8(ldg_stream(p.residual + (size_t)m * p.N + n), r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = r[i] + v[i];
+    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
+  } else {  // LIA_EPI_QKV
+    const int which = n / p.hq;
+    const int c = n - which * p.hq;
+    if (which == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = v[i] * p.q_scale;
+      *reinterpret_cast<uint4*>(p.q_out + (size_t)m * p.hq + c) = pack8(v);
+    } else {
+      const int b = m / p.S;
+      const int s = m - b * p.S;
+      bf16* cache = (which == 1) ? p.k_cache : p.v_cache;
+      const size_t row = (size_t)(p.pos0 + s) * p.cache_batch + p.b0 + b;
+      *reinterpret_cast<uint4*>(cache + row * p.hq + c) = pack8(v);
+    }
+  }
+}
+
+template <bool SWAP, int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = TILE_A * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_BYTES = SWAP ? BN * SWAP_LD * 4 : 4 * 32 * 128;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024 /* alignment slack */;
+};
+
+__host__ __device__ constexpr int tmem_cols(int bn) { return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512; }
+
+// ------------------------------------------------------------------ the kernel
+template <bool SWAP, int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p,
+                        int k_blocks, int splitk, int tiles_a, int tiles_b, float* __restrict__ ws,
+                        int* __restrict__ counters) {
+  using L = SmemLayout<SWAP, BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + L::BAR_OFFSET;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 4) * 8);
+  volatile int* flag_smem = reinterpret_cast<volatile int*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 4) * 8 + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int kbs = (k_blocks + splitk - 1) / splitk;   // k-blocks per split
+  const int total_units = SWAP ? tiles_a * splitk : tiles_a * tiles_b;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                 "r"((uint32_t)tmem_cols(BN))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto decode_unit = [&](int u, int& ta, int& tb, int& kb0, int& kb1, int& split) {
+    if (SWAP) {
+      ta = u / splitk;
+      split = u - ta * splitk;
+      tb = 0;
+      kb0 = split * kbs;
+      kb1 = min(kb0 + kbs, k_blocks);
+    } else {
+      const int group_size = GROUP_M * tiles_b;
+      const int group = u / group_size;
+      const int first = group * GROUP_M;
+      const int gm = min(GROUP_M, tiles_a - first);
+      const int r = u - group * group_size;
+      ta = first + r % gm;
+      tb = r / gm;
+      kb0 = 0;
+      kb1 = k_blocks;
+      split = 0;
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int ta, tb, kb0, kb1, split;
+        decode_unit(u, ta, tb, kb0, kb1, split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint32_t sb = sa + L::A_BYTES;
+          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+          tma_load_2d(sa, &tmA, kb * BLOCK_K, ta * TILE_A, full_bar(stage));
+          tma_load_2d(sb, &tmB, kb * BLOCK_K, tb * BN, full_bar(stage));
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(TILE_A, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int ta, tb, kb0, kb1, split;
+        decode_unit(u, ta, tb, kb0, kb1, split);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
+          const uint64_t da = make_smem_desc(sa);
+          const uint64_t db = make_smem_desc(sa + L::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
+            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        tcgen05_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp >= EPI_WARP0) {
+    // ===================== epilogue =====================
+    const int ew = warp - EPI_WARP0;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
+      int ta, tb, kb0, kb1, split;
+      decode_unit(u, ta, tb, kb0, kb1, split);
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(ew * 32) << 16);
+
+      if (!SWAP) {
+        // tile rows = tokens (TMEM lanes), columns = output features
+        const uint32_t stg = smem_base + STAGES * L::STAGE_BYTES + ew * 4096;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            uint32_t v[32];
+            tmem_ld32(taddr + c0 + half * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int chunk = half * 4 + j;
+              const uint32_t addr = stg + lane * 128 + ((chunk ^ (lane & 7)) << 4);
+              const uint32_t x0 = pack_bf16x2(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+              const uint32_t x1 = pack_bf16x2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              const uint32_t x2 = pack_bf16x2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+              const uint32_t x3 = pack_bf16x2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(x0), "r"(x1), "r"(x2), "r"(x3) : "memory");
+            }
+          }
+          if (c0 + 64 >= BN) {
+            // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+          } else {
+            __syncwarp();
+          }
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + (lane >> 3);
+            const int ch = lane & 7;
+            uint4 q;
+            const uint32_t addr = stg + r * 128 + ((ch ^ (r & 7)) << 4);
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
+            const int m = ta * TILE_A + ew * 32 + r;
+            const int n = tb * BN + c0 + ch * 8;
+            if (m < p.M && n < p.N) {
+              float f[8];
+              unpack8(q, f);
+              epilogue_store8(p, m, n, f);
+            }
+          }
+          __syncwarp();
+        }
+      } else {
+        // tile rows = output features (TMEM lanes), columns = tokens: transpose through smem / workspace
+        const int nl = ew * 32 + lane;                     // feature inside the tile
+        const int ncol = ta * TILE_A + nl;
+        float* stgf = reinterpret_cast<float*>(smem_gen + STAGES * L::STAGE_BYTES);
+        const int ldws = tiles_a * TILE_A;
+        constexpr int CH = BN >= 32 ? 32 : 16;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += CH) {
+          uint32_t v[CH];
+          if (CH == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
+          tmem_ld_wait();
+          if (splitk == 1) {
+#pragma unroll
+            for (int j = 0; j < CH; ++j) stgf[(c0 + j) * SWAP_LD + nl] = __uint_as_float(v[j]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < CH; ++j)
+              if (c0 + j < p.M) ws[((size_t)split * BN + c0 + j) * ldws + ncol] = __uint_as_float(v[j]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty_bar(acc));
+        bool do_reduce = true;
+        if (splitk > 1) {
+          __threadfence();
+          epi_bar_sync();
+          if (threadIdx.x == EPI_WARP0 * 32) {
+            const int old = atomicAdd(&counters[ta], 1);
+            const int last = (old == splitk - 1);
+            if (last) counters[ta] = 0;                    // self-reset for the next GEMM call
+            *flag_smem = last;
+          }
+          epi_bar_sync();
+          do_reduce = (*flag_smem != 0);
+          if (do_reduce) __threadfence();
+        } else {
+          epi_bar_sync();
+        }
+        if (do_reduce) {
+          const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
+          const int rows = min(BN, p.M);
+          for (int vec = et; vec < rows * (TILE_A / 8); vec += 128) {
+            const int m = vec / (TILE_A / 8);
+            const int c8 = vec - m * (TILE_A / 8);
+            const int n = ta * TILE_A + c8 * 8;
+            if (n >= p.N) continue;
+            float f[8];
+            if (splitk == 1) {
+              const float4 a = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8);
+              const float4 b = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8 + 4);
+              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = 0.f;
+              for (int s = 0; s < splitk; ++s) {             // fixed order: deterministic
+                const float* src = ws + ((size_t)s * BN + m) * ldws + n;
+                const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i]);
+            epilogue_store8(p, m, n, f);
+          }
+        }
+        epi_bar_sync();                                    // staging / flag reuse by the next unit
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor [rows, K] row-major, box = [box_rows, 64] with 128-byte swizzle; OOB -> zeros
+int make_tmap(CUtensorMap* map, const void* base, int rows, int K, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    lia_set_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return LIA_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    lia_set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows=%d K=%d box_rows=%d)", (int)r, rows, K, box_rows);
+    return LIA_ERR_CUDA;
+  }
+  return LIA_OK;
+}
+
+struct Plan {
+  bool swap;
+  int bn;
+  int splitk;
+  int tiles_a, tiles_b, k_blocks;
+};
+
+Plan make_plan(int M, int N, int K) {
+  Plan pl;
+  pl.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
+  pl.swap = (M <= 128);
+  pl.splitk = 1;
+  if (pl.swap) {
+    pl.bn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
+    pl.tiles_a = (N + TILE_A - 1) / TILE_A;
+    pl.tiles_b = 1;
+    // split K so that (almost) every SM streams weights; keep >= 4 k-blocks per split
+    const int sms = lia_sm_count();
+    double best = -1.0;
+    for (int s = 1; s <= MAX_SPLITK; ++s) {
+      if (pl.k_blocks / s < 4 && s > 1) break;
+      const int kbs = (pl.k_blocks + s - 1) / s;
+      if ((s - 1) * kbs >= pl.k_blocks) continue;          // an empty split
+      const int units = pl.tiles_a * s;
+      const int waves = (units + sms - 1) / sms;
+      const double eff = (double)units / ((double)waves * sms) - 0.01 * (s - 1);   // mild penalty per extra split
+      if (eff > best) {
+        best = eff;
+        pl.splitk = s;
+      }
+    }
+  } else {
+    pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
+    pl.tiles_a = (M + TILE_A - 1) / TILE_A;
+    pl.tiles_b = (N + pl.bn - 1) / pl.bn;
+  }
+  return pl;
+}
+
+template <bool SWAP, int BN, int STAGES>
+int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* counters,
+           cudaStream_t stream) {
+  using L = SmemLayout<SWAP, BN, STAGES>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  auto kern = lia_gemm_tcgen05_kernel<SWAP, BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int units = SWAP ? pl.tiles_a * pl.splitk : pl.tiles_a * pl.tiles_b;
+  const int grid = units < lia_sm_count() ? units : lia_sm_count();
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.splitk, pl.tiles_a, pl.tiles_b, ws, counters);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}
+
+}  // namespace
+
+extern "C" size_t lia_gemm_workspace_bytes(int M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const Plan pl = make_plan(M, N, K);
+  size_t bytes = COUNTER_BYTES;
+  if (pl.swap && pl.splitk > 1) bytes += (size_t)pl.splitk * pl.bn * pl.tiles_a * TILE_A * sizeof(float);
+  return bytes;
+}
+
+extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
+                             int N, int K, int epilogue, const LiaQkvArgs* qkv, void* workspace, size_t workspace_bytes,
+                             lia_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LIA_CHECK_ARG(M > 0 && N > 0 && K > 0, "lia_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", M, N, K);
+  LIA_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "lia_gemm_bf16: K and N must be multiples of 8 (got K=%d N=%d)", K, N);
+  LIA_CHECK_ARG(A && W, "lia_gemm_bf16: null operand");
+  LIA_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "lia_gemm_bf16: operands must be 16-byte aligned");
+  LIA_CHECK_ARG(epilogue >= LIA_EPI_BIAS && epilogue <= LIA_EPI_QKV, "lia_gemm_bf16: unknown epilogue %d", epilogue);
+  EpiParams ep{};
+  ep.bias = reinterpret_cast<const bf16*>(bias);
+  ep.residual = reinterpret_cast<const bf16*>(residual);
+  ep.out = reinterpret_cast<bf16*>(out);
+  ep.M = M;
+  ep.N = N;
+  ep.mode = epilogue;
+  if (epilogue == LIA_EPI_QKV) {
+    LIA_CHECK_ARG(qkv != nullptr, "lia_gemm_bf16: LIA_EPI_QKV needs LiaQkvArgs");
+    LIA_CHECK_ARG(qkv->hq > 0 && qkv->hq % 8 == 0 && N == 3 * qkv->hq, "lia_gemm_bf16: QKV needs N == 3*hq, hq %% 8 == 0");
+    LIA_CHECK_ARG(qkv->S > 0 && M % qkv->S == 0, "lia_gemm_bf16: QKV needs M %% S == 0");
+    LIA_CHECK_ARG(qkv->q_out && qkv->k_cache && qkv->v_cache, "lia_gemm_bf16: QKV null output");
+    LIA_CHECK_ARG(qkv->b0 >= 0 && qkv->b0 + M / qkv->S <= qkv->cache_batch && qkv->pos0 >= 0, "lia_gemm_bf16: QKV batch window");
+    ep.q_out = reinterpret_cast<bf16*>(qkv->q_out);
+    ep.k_cache = reinterpret_cast<bf16*>(qkv->k_cache);
+    ep.v_cache = reinterpret_cast<bf16*>(qkv->v_cache);
+    ep.hq = qkv->hq; ep.S = qkv->S; ep.pos0 = qkv->pos0; ep.cache_batch = qkv->cache_batch; ep.b0 = qkv->b0;
+    ep.q_scale = qkv->q_scale;
+  } else {
+    LIA_CHECK_ARG(out != nullptr, "lia_gemm_bf16: null output");
+    if (epilogue == LIA_EPI_BIAS_RESIDUAL) LIA_CHECK_ARG(residual != nullptr, "lia_gemm_bf16: residual epilogue needs residual");
+  }
+  Plan pl = make_plan(M, N, K);
+  float* ws = nullptr;
+  int* counters = nullptr;
+  if (pl.swap && pl.splitk > 1) {
+    const size_t need = COUNTER_BYTES + (size_t)pl.splitk * pl.bn * pl.tiles_a * TILE_A * sizeof(float);
+    if (workspace == nullptr || workspace_bytes < need || pl.tiles_a * (int)sizeof(int) > COUNTER_BYTES) {
+      pl.splitk = 1;   // no workspace: stream the weights with fewer CTAs rather than fail
+    } else {
+      counters = reinterpret_cast<int*>(workspace);
+      ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + COUNTER_BYTES);
+    }
+  }
+  CUtensorMap tmA, tmB;
+  int rc;
+  if (pl.swap) {
+    if ((rc = make_tmap(&tmA, W, N, K, TILE_A)) != LIA_OK) return rc;
+    if ((rc = make_tmap(&tmB, A, M, K, pl.bn)) != LIA_OK) return rc;
+    switch (pl.bn) {
+      case 16: return launch<true, 16, 8>(pl, tmA, tmB, ep, ws, counters, stream);
+      case 32: return launch<true, 32, 8>(pl, tmA, tmB, ep, ws, counters, stream);
+      case 64: return launch<true, 64, 7>(pl, tmA, tmB, ep, ws, counters, stream);
+      default: return launch<true, 128, 4>(pl, tmA, tmB, ep, ws, counters, stream);
+    }
+  } else {
+    if ((rc = make_tmap(&tmA, A, M, K, TILE_A)) != LIA_OK) return rc;
+    if ((rc = make_tmap(&tmB, W, N, K, pl.bn)) != LIA_OK) return rc;
+    if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, counters, stream);
+    return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, counters, stream);
+  }
+}

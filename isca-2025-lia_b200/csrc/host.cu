@@ -1,0 +1,134 @@
+// Host-side runtime pieces of libliab200: the pinned host arena and the layer streamer.
+//
+//   lia_host_arena_*  replaces lia/cxl/numa_alloc.c (numa_alloc_node/numa_free_node: raw pointer out,
+//                     caller frees with the size) and pin_memory() (lia/modeling_opt.py:167-227).
+//   lia_streamer_*    replaces load_layer/layer_copy (lia/modeling_opt.py:270-318: 16 copy_() calls per
+//                     layer) and the per-forward stream/buffer churn (:1195-1212, :1288-1316) with ONE
+//                     cudaMemcpyAsync per layer slab on a private copy stream, double-buffered against
+//                     the compute stream with events -- no device-wide synchronisation.
+#include <vector>
+
+#include "common.cuh"
+
+extern "C" void* lia_host_arena_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0) {
+    lia_set_error("lia_host_arena_alloc: zero bytes");
+    return nullptr;
+  }
+  cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+  if (e != cudaSuccess) {
+    lia_set_error("lia_host_arena_alloc: cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    (void)cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+extern "C" int lia_host_arena_free(void* ptr, size_t /*bytes*/) {
+  if (ptr == nullptr) return LIA_OK;
+  LIA_CUDA(cudaFreeHost(ptr));
+  return LIA_OK;
+}
+
+struct LiaStreamer {
+  std::vector<void*> slabs;
+  size_t slab_bytes = 0;
+  cudaStream_t copy_stream = nullptr;
+  std::vector<cudaEvent_t> ready;     // copy into slot finished
+  std::vector<cudaEvent_t> released;  // compute no longer reads slot
+  std::vector<bool> has_release;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+  double bytes = 0.0;
+  double copy_ms = 0.0;
+};
+
+extern "C" LiaStreamer* lia_streamer_create(void* const* device_slabs, int n_slots, size_t slab_bytes) {
+  if (device_slabs == nullptr || n_slots <= 0 || slab_bytes == 0) {
+    lia_set_error("lia_streamer_create: bad arguments");
+    return nullptr;
+  }
+  LiaStreamer* s = new (std::nothrow) LiaStreamer();
+  if (!s) {
+    lia_set_error("lia_streamer_create: out of host memory");
+    return nullptr;
+  }
+  s->slab_bytes = slab_bytes;
+  if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    lia_set_error("lia_streamer_create: cudaStreamCreate failed");
+    delete s;
+    return nullptr;
+  }
+  for (int i = 0; i < n_slots; ++i) {
+    s->slabs.push_back(device_slabs[i]);
+    cudaEvent_t a = nullptr, b = nullptr;
+    if (cudaEventCreateWithFlags(&a, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&b, cudaEventDisableTiming) != cudaSuccess) {
+      lia_set_error("lia_streamer_create: cudaEventCreate failed");
+      lia_streamer_destroy(s);
+      return nullptr;
+    }
+    s->ready.push_back(a);
+    s->released.push_back(b);
+    s->has_release.push_back(false);
+  }
+  return s;
+}
+
+extern "C" int lia_streamer_prefetch(LiaStreamer* s, int slot, const void* host_src, size_t bytes) {
+  LIA_CHECK_ARG(s && slot >= 0 && slot < (int)s->slabs.size(), "lia_streamer_prefetch: bad slot");
+  LIA_CHECK_ARG(host_src && bytes > 0 && bytes <= s->slab_bytes, "lia_streamer_prefetch: %zu bytes do not fit the %zu-byte slab", bytes, s->slab_bytes);
+  if (s->has_release[slot]) LIA_CUDA(cudaStreamWaitEvent(s->copy_stream, s->released[slot], 0));
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+  LIA_CUDA(cudaEventCreate(&t0));
+  LIA_CUDA(cudaEventCreate(&t1));
+  LIA_CUDA(cudaEventRecord(t0, s->copy_stream));
+  LIA_CUDA(cudaMemcpyAsync(s->slabs[slot], host_src, bytes, cudaMemcpyHostToDevice, s->copy_stream));
+  LIA_CUDA(cudaEventRecord(t1, s->copy_stream));
+  LIA_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
+  s->timing.emplace_back(t0, t1);
+  s->bytes += (double)bytes;
+  return LIA_OK;
+}
+
+extern "C" int lia_streamer_wait(LiaStreamer* s, int slot, lia_stream_t compute_stream) {
+  LIA_CHECK_ARG(s && slot >= 0 && slot < (int)s->slabs.size(), "lia_streamer_wait: bad slot");
+  LIA_CUDA(cudaStreamWaitEvent(reinterpret_cast<cudaStream_t>(compute_stream), s->ready[slot], 0));
+  return LIA_OK;
+}
+
+extern "C" int lia_streamer_release(LiaStreamer* s, int slot, lia_stream_t compute_stream) {
+  LIA_CHECK_ARG(s && slot >= 0 && slot < (int)s->slabs.size(), "lia_streamer_release: bad slot");
+  LIA_CUDA(cudaEventRecord(s->released[slot], reinterpret_cast<cudaStream_t>(compute_stream)));
+  s->has_release[slot] = true;
+  return LIA_OK;
+}
+
+extern "C" int lia_streamer_stats(LiaStreamer* s, double* bytes, double* copy_ms) {
+  LIA_CHECK_ARG(s != nullptr, "lia_streamer_stats: null streamer");
+  LIA_CUDA(cudaStreamSynchronize(s->copy_stream));
+  for (auto& pr : s->timing) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) s->copy_ms += ms;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  s->timing.clear();
+  if (bytes) *bytes = s->bytes;
+  if (copy_ms) *copy_ms = s->copy_ms;
+  return LIA_OK;
+}
+
+extern "C" int lia_streamer_destroy(LiaStreamer* s) {
+  if (!s) return LIA_OK;
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  for (auto& pr : s->timing) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  for (auto e : s->ready) cudaEventDestroy(e);
+  for (auto e : s->released) cudaEventDestroy(e);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+  return LIA_OK;
+}

@@ -1,0 +1,136 @@
+// Small HBM-bound kernels either side of the layer stack: embeddings, greedy argmax,
+// residual add after a tensor-parallel all-reduce.
+#include "common.cuh"
+
+namespace {
+
+// hidden[b,s,:] = embed_tokens[ids[b,s]] + embed_positions[past_len + s + 2]
+// (lia/modeling_opt.py:1107-1142; positions from an all-ones mask, :368-378, offset 2 at :365)
+__global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ tok,
+                                                    const bf16* __restrict__ pos, bf16* __restrict__ out, int S, int h,
+                                                    int past_len, int vocab, int max_pos_rows) {
+  const int row = blockIdx.x;          // b*S + s
+  const int s = row % S;
+  long long id = ids[row];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  int p = past_len + s + 2;
+  p = p >= max_pos_rows ? max_pos_rows - 1 : p;
+  const bf16* tr = tok + (size_t)id * h;
+  const bf16* pr = pos + (size_t)p * h;
+  bf16* o = out + (size_t)row * h;
+  for (int i = threadIdx.x * 8; i < h; i += 128 * 8) {
+    float a[8], c[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(tr + i)), a);
+    unpack8(__ldg(reinterpret_cast<const uint4*>(pr + i)), c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += c[j];
+    *reinterpret_cast<uint4*>(o + i) = pack8(a);
+  }
+}
+
+// next[b] = argmax_v logits[b,v], lowest index on ties, one id optionally suppressed
+// (lia/generation_utils.py:872-880 + greedy_search.py:395)
+__global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ logits, int64_t* __restrict__ next, int V,
+                                                     int suppress) {
+  __shared__ float sv[8];
+  __shared__ int si[8];
+  const bf16* row = logits + (size_t)blockIdx.x * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  const int nvec = V >> 3;
+  for (int i = threadIdx.x; i < nvec; i += 256) {
+    float f[8];
+    unpack8(ldg_stream(row + i * 8), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = i * 8 + j;
+      const float v = (idx == suppress) ? -INFINITY : f[j];
+      if (v > best || (v == best && idx < bi)) {
+        best = v;
+        bi = idx;
+      }
+    }
+  }
+  for (int idx = nvec * 8 + threadIdx.x; idx < V; idx += 256) {
+    const float v = (idx == suppress) ? -INFINITY : __bfloat162float(row[idx]);
+    if (v > best || (v == best && idx < bi)) {
+      best = v;
+      bi = idx;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) {
+      best = ov;
+      bi = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sv[threadIdx.x >> 5] = best;
+    si[threadIdx.x >> 5] = bi;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w)
+      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
+        best = sv[w];
+        bi = si[w];
+      }
+    next[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;
+  }
+}
+
+// out = bf16(residual + x): the residual add that follows the all-reduce of a row-parallel
+// projection (decoder.py:247, :317)
+__global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
+                                                           bf16* __restrict__ out, size_t nvec) {
+  for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
+    float a[8], c[8];
+    unpack8(ldg_stream(x + i * 8), a);
+    unpack8(ldg_stream(res + i * 8), c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = c[j] + a[j];
+    *reinterpret_cast<uint4*>(out + i * 8) = pack8(a);
+  }
+}
+
+}  // namespace
+
+extern "C" int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
+                              int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LIA_CHECK_ARG(ids && embed_tokens && embed_positions && out, "lia_embed_bf16: null pointer");
+  LIA_CHECK_ARG(B > 0 && S > 0 && h > 0 && h % 8 == 0, "lia_embed_bf16: bad shape B=%d S=%d h=%d", B, S, h);
+  LIA_CHECK_ARG(past_len >= 0 && past_len + S + 2 <= max_pos_rows, "lia_embed_bf16: positions %d..%d exceed the table (%d rows)", past_len + 2, past_len + S + 1, max_pos_rows);
+  embed_kernel<<<B * S, 128, 0, stream>>>(ids, reinterpret_cast<const bf16*>(embed_tokens),
+                                           reinterpret_cast<const bf16*>(embed_positions), reinterpret_cast<bf16*>(out), S, h,
+                                           past_len, vocab, max_pos_rows);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}
+
+extern "C" int lia_argmax_bf16(const void* logits, int64_t* next, int B, int V, int suppress_id, lia_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LIA_CHECK_ARG(logits && next && B > 0 && V > 0, "lia_argmax_bf16: bad arguments");
+  LIA_CHECK_ARG(((size_t)V * 2) % 16 == 0 || B == 1, "lia_argmax_bf16: V*2 must be a multiple of 16 bytes for B > 1 (V=%d)", V);
+  argmax_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const bf16*>(logits), next, V, suppress_id);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}
+
+extern "C" int lia_residual_add_bf16(const void* x, const void* residual, void* out, size_t n, lia_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LIA_CHECK_ARG(x && residual && out, "lia_residual_add_bf16: null pointer");
+  LIA_CHECK_ARG(n % 8 == 0, "lia_residual_add_bf16: n must be a multiple of 8");
+  if (n == 0) return LIA_OK;
+  const size_t nvec = n / 8;
+  size_t blocks = (nvec + 255) / 256;
+  const size_t cap = (size_t)lia_sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  residual_add_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(residual),
+                                                            reinterpret_cast<bf16*>(out), nvec);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}

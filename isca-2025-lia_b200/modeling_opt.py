@@ -1,0 +1,513 @@
+"""OPT model surface of LIA, re-built on the B200 kernels.
+
+Keeps the reference's faces:
+  * ``OPTForCausalLM.forward(input_ids, attention_mask, past_key_values, ..., prefill_policy,
+    decoding_policy, no_overlap, pin_weight, gpu_percentage, num_minibatch, enable_cxl,
+    max_new_tokens) -> (logits [B,1,V], past_key_values)``
+    (intel_extension_for_pytorch/transformers/models/reference/models.py:371-445)
+  * ``OPTDecoder.forward`` with the same kwargs (lia/modeling_opt.py:1021-1586)
+  * ``OPTDecoderLayer.forward(hidden_states, attention_mask, layer_head_mask, past_key_value,
+    output_attentions, use_cache, gpu_layer, policy, max_new_tokens)``
+    (.../reference/modules/decoder.py:172-183, 323-335)
+  * ``generate(input_ids, max_new_tokens=, min_new_tokens=, do_sample=False, num_beams=1,
+    <LIA kwargs>)`` (single_instance/run_generation.py:179-182, 319)
+  * ``past_key_values[l] = (marker, K, V, beam_idx)`` with ``marker.shape[2] == tokens cached``
+    and K/V time-major ``[S+new, B, H, d]`` (attentions.py:462-491, greedy_search.py:272-282).
+
+What differs by design: every layer op is one call into libliab200.so (no torch math on the
+path), the whole stack -- embeddings, layers, final LayerNorm, lm_head, argmax -- stays on
+the GPU, buffers/streams are allocated once (the reference re-creates them per forward,
+lia/modeling_opt.py:1180-1212), non-resident layers are streamed from pinned host memory
+instead of being computed on the CPU, and decode steps are replayed from CUDA graphs.
+
+Policy mapping: 0/2/3/4 -> all-GPU compute; 1 (full CPU, the IPEX/AMX
+baseline) is not part of this build -- ``bench.py --impl reference`` times it.
+"""
+import math
+import time
+from dataclasses import dataclass, field
+
+import torch
+
+from . import _lib, ops, tp as tp_mod
+from .ops import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV
+from .streamer import HostArena, LayerStreamer
+from .weights import LAYER_KEYS, LayerLayout, layer_from_hf_state_dict, pack_layer, random_embeddings, random_layer
+
+BF16 = torch.bfloat16
+LN_EPS = 1e-5
+
+
+@dataclass
+class OPTConfig:
+    """Fields of the HF OPTConfig that the path reads (lia/modeling_opt.py:977-1013)."""
+    hidden_size: int = 768
+    num_hidden_layers: int = 12
+    num_attention_heads: int = 12
+    ffn_dim: int = 3072
+    vocab_size: int = 50272
+    max_position_embeddings: int = 2048
+    do_layer_norm_before: bool = True
+    pad_token_id: int = 1
+    bos_token_id: int = 2
+    eos_token_id: int = 2
+    init_std: float = 0.02
+    token_latency: bool = False        # run_generation.py:153-154
+    lm_head_generation: bool = True    # run_generation.py:155-156
+    name: str = "opt"
+    architectures: list = field(default_factory=lambda: ["OPTForCausalLM"])
+
+    @property
+    def head_dim(self):
+        return self.hidden_size // self.num_attention_heads
+
+
+def _cfg(name, L, h, H, f, **kw):
+    return OPTConfig(hidden_size=h, num_hidden_layers=L, num_attention_heads=H, ffn_dim=f, name=name, **kw)
+
+
+# SURVEY.md A.1; 66b/175b from utils/opt-weight-gen.py:83-131
+OPT_CONFIGS = {
+    "opt-125m": _cfg("opt-125m", 12, 768, 12, 3072),
+    "opt-1.3b": _cfg("opt-1.3b", 24, 2048, 32, 8192),
+    "opt-6.7b": _cfg("opt-6.7b", 32, 4096, 32, 16384),
+    "opt-13b": _cfg("opt-13b", 40, 5120, 40, 20480),
+    "opt-30b": _cfg("opt-30b", 48, 7168, 56, 28672),
+    "opt-66b": _cfg("opt-66b", 64, 9216, 72, 36864),
+    "opt-175b": _cfg("opt-175b", 96, 12288, 96, 49152),
+}
+
+
+def get_config(name_or_path):
+    key = str(name_or_path).rstrip("/").split("/")[-1].lower()
+    if key not in OPT_CONFIGS:
+        raise KeyError(f"unknown OPT model {name_or_path!r}; known: {sorted(OPT_CONFIGS)}")
+    c = OPT_CONFIGS[key]
+    return OPTConfig(**{k: getattr(c, k) for k in c.__dataclass_fields__})
+
+
+def _check_policy(p, what):
+    if p is None:
+        return 3
+    if p == 1:
+        raise NotImplementedError(
+            f"{what}=1 is the reference's full-CPU (IPEX/AMX) policy; this build has no CPU compute path. "
+            "It is timed as the reported baseline by `bench.py --impl reference`.")
+    if p not in (0, 2, 3, 4):
+        raise ValueError(f"{what} must be one of 0,1,2,3,4 (got {p})")
+    return p
+
+
+class _Workspace:
+    """Activation scratch for up to ``rows`` token rows -- allocated once per shape."""
+
+    def __init__(self, cfg, layout, rows, batch, device):
+        h, hq, fq = cfg.hidden_size, layout.hq, layout.fq
+        e = lambda *s: torch.empty(*s, dtype=BF16, device=device)  # noqa: E731
+        self.rows = rows
+        self.ln, self.q, self.ctx, self.x1, self.ffn = e(rows, h), e(rows, hq), e(rows, hq), e(rows, h), e(rows, fq)
+        self.tp = e(rows, h) if layout.tp > 1 else None
+        shapes = []
+        for m in {rows, batch}:
+            shapes += [(m, 3 * hq, h), (m, h, hq), (m, fq, h), (m, h, fq), (m, cfg.vocab_size, h)]
+        self.gemm = ops.GemmWorkspace(ops.GemmWorkspace.bytes_for(shapes), device)
+        self.attn = ops.attn_decode_workspace(batch, cfg.num_attention_heads // layout.tp, cfg.head_dim, device)
+
+
+class _GenState:
+    """Everything one (B, S, new) generation shape needs, kept across generate() calls."""
+
+    def __init__(self, model, B, S, new, num_minibatch):
+        cfg, dev = model.config, model.device
+        L, d = cfg.num_hidden_layers, cfg.head_dim
+        Hl = cfg.num_attention_heads // model.tp_world
+        self.B, self.S, self.new = B, S, new
+        self.Tmax = S + new
+        self.kc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) for _ in range(L)]
+        self.vc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) for _ in range(L)]
+        self.beam_idx = torch.zeros(self.Tmax, B, dtype=torch.long, device=dev)
+        self.prompt = torch.zeros(B, S, dtype=torch.int64, device=dev)
+        self.steps_tok = torch.zeros(max(new, 1), B, dtype=torch.int64, device=dev)
+        self.x = torch.empty(B * S, cfg.hidden_size, dtype=BF16, device=dev)
+        self.xd = torch.empty(B, cfg.hidden_size, dtype=BF16, device=dev)
+        self.xn = torch.empty(B, cfg.hidden_size, dtype=BF16, device=dev)
+        self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
+        mb = max(1, B // max(1, num_minibatch))
+        self.ws = _Workspace(cfg, model.layout, max(mb * S, B), B, dev)
+        self.graphs = {}
+        self.calls = 0
+
+    def past_key_values(self, T):
+        marker = torch.empty(1, T, T, 1, dtype=torch.long, device="meta")   # only .shape is ever read (M:1111)
+        return tuple((marker, k, v, self.beam_idx) for k, v in zip(self.kc, self.vc))
+
+
+class OPTDecoderLayer:
+    """decoder.py:172-335 (+ attentions.py:312-557) as seven kernel launches."""
+
+    def __init__(self, decoder, idx):
+        self.decoder, self.idx = decoder, idx
+        self.do_layer_norm_before = True
+        self.distributed = decoder.tp_world > 1
+
+    # ---- the reference's layer face
+    def forward(self, hidden_states, attention_mask=None, layer_head_mask=None, past_key_value=None,
+                output_attentions=False, use_cache=False, gpu_layer=None, policy=0, max_new_tokens=None):
+        if layer_head_mask is not None or output_attentions:
+            raise NotImplementedError("layer_head_mask / output_attentions are not supported on the GPU path")
+        _check_policy(policy, "policy")
+        dec = self.decoder
+        B, S, h = hidden_states.shape
+        views = self._views_from_gpu_layer(gpu_layer) if gpu_layer is not None else dec.layer_views(self.idx)
+        past_len = 0 if past_key_value is None else int(past_key_value[0].shape[2])
+        Hl, d = dec.config.num_attention_heads // dec.tp_world, dec.config.head_dim
+        if S != 1:
+            if past_len != 0:
+                raise NotImplementedError("multi-token forward with a non-empty KV cache is not supported")
+            tmax = S + (max_new_tokens if max_new_tokens is not None else dec.config.max_position_embeddings - S)
+            kc = torch.zeros(tmax, B, Hl, d, dtype=BF16, device=hidden_states.device)   # attentions.py:471-472
+            vc = torch.zeros_like(kc)
+            beam = torch.zeros(tmax, B, dtype=torch.long, device=hidden_states.device)
+        else:
+            kc, vc, beam = past_key_value[1], past_key_value[2], past_key_value[3]
+        x = hidden_states.reshape(B * S, h).clone()
+        ws = dec.workspace(B * S, B)
+        dec.layer_rows(views, x, kc, vc, B, S, past_len, 0, ws)
+        T = past_len + S
+        present = (torch.empty(1, T, T, 1, dtype=torch.long, device="meta"), kc, vc, beam)
+        outputs = (x.view(B, S, h),)
+        if use_cache:
+            outputs += (present,)
+        if policy == 0:                                                   # decoder.py:331-333
+            outputs += (kc[past_len:T], vc[past_len:T])
+        return outputs
+
+    __call__ = forward
+
+    def _views_from_gpu_layer(self, gl):
+        """16-entry list in the reference's order (lia/modeling_opt.py:272-293) -> fused views."""
+        if len(gl) != 16:
+            raise ValueError("gpu_layer must have 16 entries (ln1 w/b, q w/b, k w/b, v w/b, out w/b, ln2 w/b, fc1 w/b, fc2 w/b)")
+        w = dict(zip(LAYER_KEYS, gl))
+        return {"ln1_w": w["ln1_w"], "ln1_b": w["ln1_b"],
+                "qkv_w": torch.cat([w["q_w"], w["k_w"], w["v_w"]], 0).contiguous(),
+                "qkv_b": torch.cat([w["q_b"], w["k_b"], w["v_b"]], 0).contiguous(),
+                "o_w": w["o_w"], "o_b": w["o_b"], "ln2_w": w["ln2_w"], "ln2_b": w["ln2_b"],
+                "fc1_w": w["fc1_w"], "fc1_b": w["fc1_b"], "fc2_w": w["fc2_w"], "fc2_b": w["fc2_b"]}
+
+
+class OPTDecoder:
+    """lia/modeling_opt.py:977-1586: embeddings, layer placement, streaming, layer loop, final LN."""
+
+    def __init__(self, config, device, tp_rank=0, tp_world=1):
+        self.config, self.device = config, torch.device(device)
+        self.tp_rank, self.tp_world = tp_rank, tp_world
+        if config.head_dim not in (64, 128):
+            raise NotImplementedError(f"head_dim {config.head_dim} unsupported (kernels handle 64 and 128)")
+        if config.num_attention_heads % tp_world or config.ffn_dim % tp_world:
+            raise ValueError("heads and ffn_dim must divide by the tensor-parallel world size")
+        self.layout = LayerLayout(config.hidden_size, config.ffn_dim, tp_world)
+        self.layers = [OPTDecoderLayer(self, i) for i in range(config.num_hidden_layers)]
+        self.scaling = config.head_dim ** -0.5                      # lia/modeling_opt.py:413
+        self.embed_tokens = self.embed_positions = self.final_ln_w = self.final_ln_b = None
+        self.n_resident = 0
+        self.resident = []          # flat device slabs
+        self.resident_views = []
+        self.host_arena = None
+        self.host_slabs = []
+        self.streamer = None
+        self._ws = {}
+
+    # ---- weights & placement (move_gpu_layer / pin_memory, lia/modeling_opt.py:167-268)
+    def load_layers(self, layer_fn, gpu_percentage=100):
+        """``layer_fn(i, device)`` -> full layer dict on ``device``; resident layers are packed on the
+        GPU, the rest straight into the pinned host arena."""
+        L = self.config.num_hidden_layers
+        n_res = L if gpu_percentage >= 100 else int(L * gpu_percentage / 100)   # M:1182 (100 == intended "all")
+        self.n_resident = n_res
+        self.resident, self.resident_views, self.host_slabs = [], [], []
+        if self.streamer is not None:
+            self.streamer.close()
+            self.streamer = None
+        n_host = L - n_res
+        if n_host:
+            self.host_arena = HostArena(self.layout.numel * n_host)
+        for i in range(L):
+            if i < n_res:
+                slab = pack_layer(layer_fn(i, self.device), self.layout, self.tp_rank)
+                self.resident.append(slab)
+                self.resident_views.append(self.layout.views(slab))
+            else:
+                j = i - n_res
+                dst = self.host_arena.tensor[j * self.layout.numel:(j + 1) * self.layout.numel]
+                dst.copy_(pack_layer(layer_fn(i, self.device), self.layout, self.tp_rank))
+                self.host_slabs.append(dst)
+        if n_host:
+            torch.cuda.synchronize(self.device)
+            self.streamer = LayerStreamer(self.layout, self.host_slabs, self.device)
+
+    def load_embeddings(self, e):
+        dev = self.device
+        self.embed_tokens = e["embed_tokens"].to(dev, BF16).contiguous()
+        self.embed_positions = e["embed_positions"].to(dev, BF16).contiguous()
+        self.final_ln_w = e["final_ln_w"].to(dev, BF16).contiguous()
+        self.final_ln_b = e["final_ln_b"].to(dev, BF16).contiguous()
+
+    def check_gpu_percentage(self, gpu_percentage):
+        if gpu_percentage is None:
+            return
+        L = self.config.num_hidden_layers
+        want = L if gpu_percentage >= 100 else int(L * gpu_percentage / 100)
+        if want != self.n_resident:
+            raise ValueError(f"model was placed with {self.n_resident} resident layers but gpu_percentage="
+                             f"{gpu_percentage} asks for {want}; reload with load_layers(..., gpu_percentage=)")
+
+    def layer_views(self, i):
+        if i < self.n_resident:
+            return self.resident_views[i]
+        raise RuntimeError(f"layer {i} is streamed; call it through OPTDecoder.forward")
+
+    def workspace(self, rows, batch):
+        key = (rows, batch)
+        if key not in self._ws:
+            self._ws[key] = _Workspace(self.config, self.layout, rows, batch, self.device)
+        return self._ws[key]
+
+    # ---- one layer over a block of token rows (rows are [b-major, S] and updated in place)
+    def layer_rows(self, v, rows, kc, vc, nb, S, pos0, b0, ws):
+        M = nb * S
+        ln, q, ctx, x1, ffn = ws.ln[:M], ws.q[:M], ws.ctx[:M], ws.x1[:M], ws.ffn[:M]
+        ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                   # decoder.py:204
+        ops.gemm(ln, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                                        # attentions.py:376-491
+                 qkv=ops.qkv_args(q, kc, vc, S, pos0, b0, self.scaling), workspace=ws.gemm)
+        if S != 1:
+            ops.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
+        else:
+            ops.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
+        if self.tp_world == 1:
+            ops.gemm(ctx, v["o_w"], v["o_b"], out=x1, epilogue=EPI_BIAS_RESIDUAL, residual=rows, workspace=ws.gemm)  # decoder.py:228-229
+        else:
+            part = ws.tp[:M]
+            ops.gemm(ctx, v["o_w"], v["o_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)        # decoder.py:60-68
+            tp_mod.all_reduce(part)
+            ops.residual_add(part, rows, out=x1)                                                      # decoder.py:247
+        ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                     # decoder.py:272
+        ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)      # decoder.py:285
+        if self.tp_world == 1:
+            ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=rows, epilogue=EPI_BIAS_RESIDUAL, residual=x1, workspace=ws.gemm)  # decoder.py:309-310
+        else:
+            part = ws.tp[:M]
+            ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)
+            tp_mod.all_reduce(part)
+            ops.residual_add(part, x1, out=rows)                                                      # decoder.py:317
+
+    def run_layers(self, x, kcs, vcs, B, S, pos0, num_minibatch, ws):
+        """Layer-major, minibatch-minor loop (lia/modeling_opt.py:1222, 1284) with double-buffered
+        weight streaming for non-resident layers."""
+        mb = B if S == 1 else max(1, B // max(1, num_minibatch or 1))      # M:1178
+        if self.streamer is not None:
+            self.streamer.begin()
+        for li in range(self.config.num_hidden_layers):
+            streamed = li >= self.n_resident
+            v = self.streamer.acquire(li - self.n_resident) if streamed else self.resident_views[li]
+            for b0 in range(0, B, mb):
+                nb = min(mb, B - b0)
+                self.layer_rows(v, x[b0 * S:(b0 + nb) * S], kcs[li], vcs[li], nb, S, pos0, b0, ws)
+            if streamed:
+                self.streamer.release(li - self.n_resident)
+
+    # ---- the reference's decoder face
+    def forward(self, input_ids=None, attention_mask=None, head_mask=None, past_key_values=None, inputs_embeds=None,
+                use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=False,
+                prefill_policy=None, decoding_policy=None, no_overlap=None, pin_weight=None, gpu_percentage=None,
+                num_minibatch=None, enable_cxl=None, max_new_tokens=None):
+        if head_mask is not None or inputs_embeds is not None or output_attentions or output_hidden_states:
+            raise NotImplementedError("head_mask / inputs_embeds / output_attentions / output_hidden_states")
+        _check_policy(prefill_policy, "prefill_policy")
+        _check_policy(decoding_policy, "decoding_policy")
+        self.check_gpu_percentage(gpu_percentage)
+        ids = input_ids.to(self.device, torch.int64).contiguous()
+        B, S = ids.shape
+        past_len = int(past_key_values[0][0].shape[2]) if past_key_values is not None else 0   # M:1111
+        if attention_mask is not None and attention_mask.shape[1] != past_len + S:
+            raise ValueError(f"The provided attention mask has length {attention_mask.shape[1]}, but its length should "
+                             f"be {past_len + S} (sum of the lengths of current and past inputs)")             # M:1127-1131
+        cfg = self.config
+        if S != 1:
+            if past_len != 0:
+                raise NotImplementedError("multi-token forward with a non-empty KV cache is not supported")
+            new = max_new_tokens if max_new_tokens is not None else cfg.max_position_embeddings - S
+            Hl = cfg.num_attention_heads // self.tp_world
+            kcs = [torch.zeros(S + new, B, Hl, cfg.head_dim, dtype=BF16, device=self.device) for _ in self.layers]
+            vcs = [torch.zeros_like(k) for k in kcs]
+            beam = torch.zeros(S + new, B, dtype=torch.long, device=self.device)
+        else:
+            kcs = [p[1] for p in past_key_values]
+            vcs = [p[2] for p in past_key_values]
+            beam = past_key_values[0][3]
+        mb = B if S == 1 else max(1, B // max(1, num_minibatch or 1))
+        ws = self.workspace(max(mb * S, B), B)
+        x = ops.embed(ids, self.embed_tokens, self.embed_positions, past_len).view(B * S, cfg.hidden_size)   # M:1107-1142
+        self.run_layers(x, kcs, vcs, B, S, past_len, num_minibatch, ws)
+        hidden = ops.layernorm(x, self.final_ln_w, self.final_ln_b, LN_EPS).view(B, S, cfg.hidden_size)       # M:1563-1564
+        T = past_len + S
+        marker = torch.empty(1, T, T, 1, dtype=torch.long, device="meta")
+        next_cache = tuple((marker, k, v, beam) for k, v in zip(kcs, vcs))
+        return (hidden, next_cache)
+
+    __call__ = forward
+
+
+class _Model:
+    def __init__(self, decoder):
+        self.decoder = decoder
+
+
+class OPTForCausalLM:
+    """models.py:371-445 + the greedy loop of generation/greedy_search.py:37-460."""
+
+    def __init__(self, config, device="cuda", tp_rank=0, tp_world=1):
+        _lib.load()                                   # fail loudly if the CUDA library is missing
+        self.config = config
+        self.device = torch.device(device)
+        self.tp_rank, self.tp_world = tp_rank, tp_world
+        self.model = _Model(OPTDecoder(config, self.device, tp_rank, tp_world))
+        self.layout = self.model.decoder.layout
+        self._states = {}
+        self.use_cuda_graphs = True
+        self.last_timing = None
+
+    # ---- weights
+    def init_weights(self, seed=0, kind="normal", gpu_percentage=100, bias_std=0.0, ln_std=0.0):
+        """Random-init (lia/modeling_opt.py:895-904) or dummy (utils/opt-weight-gen.py:61-62) weights,
+        generated layer by layer on the GPU from per-layer seeds (identical on every TP rank)."""
+        cfg = self.config
+        dec = self.model.decoder
+        dec.load_embeddings(random_embeddings(cfg.vocab_size, cfg.hidden_size, cfg.max_position_embeddings,
+                                              seed * 100003 + 17, self.device, kind, cfg.init_std, ln_std, cfg.pad_token_id))
+        dec.load_layers(lambda i, dev: random_layer(cfg.hidden_size, cfg.ffn_dim, seed * 100003 + 1000 + i, dev, kind,
+                                                    cfg.init_std, bias_std, ln_std), gpu_percentage)
+        return self
+
+    def load_state_dict(self, sd, gpu_percentage=100):
+        """HF OPT names (``model.decoder.layers.{i}.self_attn.q_proj.weight`` ...)."""
+        dec = self.model.decoder
+        dec.load_embeddings({"embed_tokens": sd["model.decoder.embed_tokens.weight"],
+                             "embed_positions": sd["model.decoder.embed_positions.weight"],
+                             "final_ln_w": sd["model.decoder.final_layer_norm.weight"],
+                             "final_ln_b": sd["model.decoder.final_layer_norm.bias"]})
+        dec.load_layers(lambda i, dev: {k: t.to(dev, BF16) for k, t in layer_from_hf_state_dict(sd, i).items()},
+                        gpu_percentage)
+        return self
+
+    def eval(self):
+        return self
+
+    # ---- reference forward face
+    def forward(self, input_ids=None, attention_mask=None, past_key_values=None, head_mask=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=False,
+                prefill_policy=None, decoding_policy=None, no_overlap=None, pin_weight=None, gpu_percentage=None,
+                num_minibatch=None, enable_cxl=None, max_new_tokens=None):
+        if labels is not None:
+            raise NotImplementedError("labels / loss: inference-only build")
+        hidden, cache = self.model.decoder(
+            input_ids=input_ids, attention_mask=attention_mask, head_mask=head_mask, past_key_values=past_key_values,
+            inputs_embeds=inputs_embeds, use_cache=use_cache, output_attentions=output_attentions,
+            output_hidden_states=output_hidden_states, prefill_policy=prefill_policy, decoding_policy=decoding_policy,
+            no_overlap=no_overlap, pin_weight=pin_weight, gpu_percentage=gpu_percentage, num_minibatch=num_minibatch,
+            enable_cxl=enable_cxl, max_new_tokens=max_new_tokens)
+        if self.config.lm_head_generation and hidden.size(1) != 1:                       # models.py:424-431
+            hidden = hidden[:, -1:, :]
+        B, S, h = hidden.shape
+        logits = self.lm_head(hidden.reshape(B * S, h).contiguous()).view(B, S, self.config.vocab_size)
+        return (logits, cache)
+
+    __call__ = forward
+
+    def lm_head(self, rows, out=None, ws=None):
+        """Tied lm_head (lia/modeling_opt.py:1660), no bias: one GEMM against embed_tokens."""
+        dec = self.model.decoder
+        ws = ws or dec.workspace(rows.shape[0], rows.shape[0])
+        return ops.gemm(rows, dec.embed_tokens, None, out=out, epilogue=EPI_BIAS, workspace=ws.gemm)
+
+    # ---- generation
+    def _state(self, B, S, new, num_minibatch):
+        key = (B, S, new, num_minibatch)
+        if key not in self._states:
+            self._states.clear()                      # one live shape at a time: caches are large
+            self._states[key] = _GenState(self, B, S, new, num_minibatch)
+        return self._states[key]
+
+    def _head_and_pick(self, st, rows, t, suppress):
+        dec = self.model.decoder
+        ops.layernorm(rows, dec.final_ln_w, dec.final_ln_b, LN_EPS, out=st.xn)           # M:1563-1564 (last position)
+        self.lm_head(st.xn, out=st.logits, ws=st.ws)                                      # models.py:431
+        ops.argmax(st.logits, suppress, out=st.steps_tok[t])                              # greedy_search.py:367-395
+
+    def _prefill(self, st, num_minibatch, suppress):
+        dec, cfg = self.model.decoder, self.config
+        B, S = st.B, st.S
+        ops.embed(st.prompt, dec.embed_tokens, dec.embed_positions, 0, out=st.x.view(B, S, cfg.hidden_size))
+        dec.run_layers(st.x, st.kc, st.vc, B, S, 0, num_minibatch, st.ws)
+        st.xd.copy_(st.x.view(B, S, cfg.hidden_size)[:, -1, :])                           # models.py:430 last token only
+        self._head_and_pick(st, st.xd, 0, suppress)
+
+    def _decode_step(self, st, t, suppress):
+        """Generate token t (>= 1) from token t-1; cache holds S + t - 1 positions."""
+        dec, cfg = self.model.decoder, self.config
+        past = st.S + t - 1
+        ops.embed(st.steps_tok[t - 1].view(st.B, 1), dec.embed_tokens, dec.embed_positions, past,
+                  out=st.xd.view(st.B, 1, cfg.hidden_size))
+        dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws)
+        self._head_and_pick(st, st.xd, t, suppress)
+
+    def generate(self, input_ids, max_new_tokens=32, min_new_tokens=None, do_sample=False, num_beams=1,
+                 temperature=None, attention_mask=None, prefill_policy=None, decoding_policy=None, no_overlap=None,
+                 pin_weight=None, gpu_percentage=None, num_minibatch=None, enable_cxl=None, **unused):
+        """Greedy generation (run_generation.py:179-182: do_sample=False, num_beams=1,
+        min_new_tokens == max_new_tokens).  Returns ids [B, S+new] on ``input_ids.device`` -- and the
+        per-token latency list when ``config.token_latency`` (greedy_search.py:455-456).  Length is
+        the only stop criterion (greedy_search.py:425); eos is suppressed while fewer than
+        ``min_new_tokens`` tokens exist (generation_utils.py:872-880)."""
+        if do_sample or num_beams != 1:
+            raise NotImplementedError("only greedy search (do_sample=False, num_beams=1) is implemented")
+        _check_policy(prefill_policy, "prefill_policy")
+        _check_policy(decoding_policy, "decoding_policy")
+        dec = self.model.decoder
+        dec.check_gpu_percentage(gpu_percentage)
+        num_minibatch = int(num_minibatch or 1)
+        B, S = input_ids.shape
+        new = int(max_new_tokens)
+        if S + new > self.config.max_position_embeddings:
+            raise ValueError(f"S + max_new_tokens = {S + new} exceeds max_position_embeddings")
+        min_new = int(min_new_tokens or 0)
+        st = self._state(B, S, new, num_minibatch)
+        st.calls += 1
+        eos = self.config.eos_token_id
+        graphs_ok = self.use_cuda_graphs and dec.streamer is None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(new + 1)]
+        st.prompt.copy_(input_ids, non_blocking=True)                                    # H2D (pinned host -> HBM)
+        ev[0].record()
+        self._prefill(st, num_minibatch, eos if 0 < min_new else -1)
+        ev[1].record()
+        for t in range(1, new):
+            suppress = eos if t < min_new else -1
+            if graphs_ok and st.calls >= 2:
+                g = st.graphs.get((t, suppress))
+                if g is None:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._decode_step(st, t, suppress)
+                    st.graphs[(t, suppress)] = g
+                g.replay()
+            else:
+                self._decode_step(st, t, suppress)
+            ev[t + 1].record()
+        out_dev = torch.cat([st.prompt, st.steps_tok[:new].t()], dim=1)
+        out = out_dev.to(input_ids.device)                                               # D2H of the result (syncs)
+        torch.cuda.synchronize(self.device)
+        lat = [ev[i].elapsed_time(ev[i + 1]) / 1e3 for i in range(new)]
+        self.last_timing = {"prefill_s": lat[0], "decode_s": lat[1:], "total_s": sum(lat)}
+        if self.config.token_latency:
+            return out, lat
+        return out

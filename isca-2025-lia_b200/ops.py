@@ -1,0 +1,157 @@
+"""Tensor-level wrappers over the C ABI (include/lia_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every op below is one
+call into libliab200.so on ``torch.cuda.current_stream()``.  No op has a PyTorch
+fallback -- a missing library or a non-CUDA tensor raises.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV, LiaQkvArgs, check  # noqa: F401
+
+BF16 = torch.bfloat16
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return t.data_ptr() if t is not None else None
+
+
+def _req(t, name, dtype=BF16):
+    if not (t.is_cuda and t.dtype == dtype and t.is_contiguous()):
+        raise _lib.LiaError(f"{name}: need a contiguous CUDA {dtype} tensor, got {t.dtype} on {t.device} "
+                            f"contiguous={t.is_contiguous()}")
+    return t
+
+
+def count_launches(n=1):
+    _lib.launch_count += n
+
+
+def layernorm(x, w, b, eps=1e-5, out=None):
+    """F.layer_norm over the last dim (decoder.py:107-119)."""
+    _req(x, "x"); _req(w, "w"); _req(b, "b")
+    h = x.shape[-1]
+    rows = x.numel() // h
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().lia_layernorm_bf16(_p(x), _p(w), _p(b), _p(_req(out, "out")), rows, h, eps, _stream()),
+          "lia_layernorm_bf16")
+    count_launches()
+    return out
+
+
+class GemmWorkspace:
+    """Split-K workspace, zero-initialised once (the kernel leaves its counters zeroed)."""
+
+    def __init__(self, nbytes, device):
+        self.buf = torch.zeros(max(int(nbytes), 16384), dtype=torch.uint8, device=device)
+
+    @staticmethod
+    def bytes_for(shapes):
+        lib = _lib.load()
+        return max([lib.lia_gemm_workspace_bytes(m, n, k) for (m, n, k) in shapes] + [16384])
+
+
+def gemm(a, w, bias, out=None, epilogue=EPI_BIAS, residual=None, qkv=None, workspace=None):
+    """out = epilogue(a @ w.T) -- a [M,K], w [N,K] (decoder.py:79-105, attentions.py:376-418)."""
+    _req(a, "a"); _req(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.LiaError(f"gemm: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if bias is not None:
+        _req(bias, "bias")
+    if residual is not None:
+        _req(residual, "residual")
+    if epilogue != EPI_QKV and out is None:
+        out = torch.empty(M, N, dtype=BF16, device=a.device)
+    ws_ptr, ws_bytes = (None, 0)
+    if workspace is not None:
+        ws_ptr, ws_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
+    check(_lib.load().lia_gemm_bf16(_p(a), _p(w), _p(bias), _p(residual), _p(out), M, N, K, epilogue,
+                                    ctypes.byref(qkv) if qkv is not None else None, ws_ptr, ws_bytes, _stream()),
+          "lia_gemm_bf16")
+    count_launches()
+    return out
+
+
+def qkv_args(q_out, k_cache, v_cache, S, pos0, b0, scale):
+    """k_cache/v_cache: [Tmax, Bc, H, d] time-major (attentions.py:471-472)."""
+    _req(q_out, "q_out"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
+    hq = k_cache.shape[2] * k_cache.shape[3]
+    return LiaQkvArgs(q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), hq, S, pos0, k_cache.shape[1], b0,
+                      float(scale))
+
+
+def attn_prefill(q, k_cache, v_cache, B, S, b0=0, out=None):
+    """Causal attention over rows [0,S) of the cache (attentions.py:444-449, 493-536)."""
+    _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
+    _, Bc, H, d = k_cache.shape
+    if out is None:
+        out = torch.empty(B * S, H * d, dtype=BF16, device=q.device)
+    check(_lib.load().lia_attn_prefill_bf16(_p(q), _p(k_cache), _p(v_cache), _p(_req(out, "out")), B, H, S, d, Bc, b0,
+                                            _stream()), "lia_attn_prefill_bf16")
+    count_launches()
+    return out
+
+
+def attn_decode(q, k_cache, v_cache, B, T, b0=0, out=None, splits=0, workspace=None):
+    """One query token per sequence over T cached positions, no mask (attentions.py:395-399, 500)."""
+    _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
+    _, Bc, H, d = k_cache.shape
+    if out is None:
+        out = torch.empty(B, H * d, dtype=BF16, device=q.device)
+    ws_ptr, ws_bytes = (None, 0)
+    if workspace is not None:
+        ws_ptr, ws_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    check(_lib.load().lia_attn_decode_bf16(_p(q), _p(k_cache), _p(v_cache), _p(_req(out, "out")), B, H, T, d, Bc, b0,
+                                           splits, ws_ptr, ws_bytes, _stream()), "lia_attn_decode_bf16")
+    count_launches(2 if splits != 1 and workspace is not None else 1)
+    return out
+
+
+def attn_decode_workspace(B, H, d, device, max_splits=32):
+    n = _lib.load().lia_attn_decode_workspace_bytes(B, H, d, max_splits)
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+def embed(ids, embed_tokens, embed_positions, past_len, out=None):
+    """Token + learned positional embedding (lia/modeling_opt.py:1107-1142, 368-378)."""
+    _req(ids, "ids", torch.int64); _req(embed_tokens, "embed_tokens"); _req(embed_positions, "embed_positions")
+    B, S = ids.shape
+    V, h = embed_tokens.shape
+    if out is None:
+        out = torch.empty(B, S, h, dtype=BF16, device=ids.device)
+    check(_lib.load().lia_embed_bf16(_p(ids), _p(embed_tokens), _p(embed_positions), _p(_req(out, "out")), B, S, h,
+                                     past_len, V, embed_positions.shape[0], _stream()), "lia_embed_bf16")
+    count_launches()
+    return out
+
+
+def argmax(logits, suppress_id=-1, out=None):
+    """Greedy pick with one suppressed id (generation_utils.py:872-880, greedy_search.py:395)."""
+    _req(logits, "logits")
+    B, V = logits.shape
+    if out is None:
+        out = torch.empty(B, dtype=torch.int64, device=logits.device)
+    check(_lib.load().lia_argmax_bf16(_p(logits), _p(_req(out, "out", torch.int64)), B, V, suppress_id, _stream()),
+          "lia_argmax_bf16")
+    count_launches()
+    return out
+
+
+def residual_add(x, residual, out=None):
+    """out = residual + x after a tensor-parallel all-reduce (decoder.py:247, 317)."""
+    _req(x, "x"); _req(residual, "residual")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().lia_residual_add_bf16(_p(x), _p(residual), _p(_req(out, "out")), x.numel(), _stream()),
+          "lia_residual_add_bf16")
+    count_launches()
+    return out
