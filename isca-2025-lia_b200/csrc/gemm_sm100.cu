@@ -25,6 +25,8 @@
 //       r1 = bf16(acc); r2 = bf16(r1 + bias); then relu | bf16(residual + r2) | bf16(r2*scale).
 #include <cuda.h>
 
+#include <stdlib.h>
+
 #include <mutex>
 
 #include "common.cuh"
@@ -511,6 +513,8 @@ Plan make_plan(int M, int N, int K) {
     // split K so that (almost) every SM streams weights; keep >= 4 k-blocks per split
     const int sms = lia_sm_count();
     double best = -1.0;
+    const char* force = getenv("LIA_SPLITK");   // tuning/debug override
+    const int forced = force ? atoi(force) : 0;
     for (int s = 1; s <= MAX_SPLITK; ++s) {
       if (pl.k_blocks / s < 4 && s > 1) break;
       const int kbs = (pl.k_blocks + s - 1) / s;
@@ -522,6 +526,10 @@ Plan make_plan(int M, int N, int K) {
         best = eff;
         pl.splitk = s;
       }
+    }
+    if (forced >= 1 && forced <= MAX_SPLITK && pl.k_blocks / forced >= 1) {
+      const int kbs = (pl.k_blocks + forced - 1) / forced;
+      if ((forced - 1) * kbs < pl.k_blocks) pl.splitk = forced;
     }
   } else {
     pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
