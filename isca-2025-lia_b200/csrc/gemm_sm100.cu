@@ -39,7 +39,6 @@ constexpr int TILE_A = 128;   // rows of the UMMA "A" operand per tile (UMMA M)
 constexpr int NUM_THREADS = 256;
 constexpr int EPI_WARP0 = 4;
 constexpr int GROUP_M = 16;   // raster group (A tiles per group) for L2 reuse in NORMAL mode
-constexpr int MAX_SPLITK = 8;
 constexpr int COUNTER_BYTES = 16384;
 constexpr int SWAP_LD = TILE_A + 4;   // fp32 staging pitch (floats) in SWAP mode
 
@@ -186,12 +185,79 @@ struct SmemLayout {
 
 __host__ __device__ constexpr int tmem_cols(int bn) { return 2 * bn <= 32 ? 32 : 2 * bn <= 64 ? 64 : 2 * bn <= 128 ? 128 : 2 * bn <= 256 ? 256 : 512; }
 
+// ------------------------------------------------------------------ work scheduling
+// NORMAL: unit u = blockIdx.x + i*gridDim.x over (A tile, B tile) pairs, rastered in groups of
+//         GROUP_M A-tiles so that concurrently running CTAs share operands through L2.
+// SWAP  : "stream-K".  The iteration space is the flat list of (W row-tile, k-block) pairs; CTA c
+//         owns the contiguous span [c*total/G, (c+1)*total/G), so EVERY SM streams the same number
+//         of weight bytes whatever N and K are.  A span covers at most one trailing piece of a
+//         tile (kb0 > 0: written to this CTA's fp32 workspace slot), whole tiles, and at most one
+//         leading piece (kb0 == 0, kb1 < k_blocks: this CTA owns the tile and adds the pieces of
+//         CTAs c+1, c+2, ... in k order -- a fixed order, so results are deterministic).
+struct Work {
+  int ta, tb, kb0, kb1;
+};
+
+template <bool SWAP>
+struct Sched {
+  int k_blocks, tiles_a, tiles_b;
+  long long pos, end;   // SWAP: flat k-block position; NORMAL: unit index / count
+  __device__ Sched(int k_blocks_, int tiles_a_, int tiles_b_, int streamk) : k_blocks(k_blocks_), tiles_a(tiles_a_), tiles_b(tiles_b_) {
+    if (SWAP) {
+      if (streamk) {
+        const long long total = (long long)tiles_a * k_blocks;
+        pos = total * blockIdx.x / gridDim.x;
+        end = total * (blockIdx.x + 1) / gridDim.x;
+      } else {   // whole tiles only
+        pos = ((long long)tiles_a * blockIdx.x / gridDim.x) * k_blocks;
+        end = ((long long)tiles_a * (blockIdx.x + 1) / gridDim.x) * k_blocks;
+      }
+    } else {
+      pos = blockIdx.x;
+      end = (long long)tiles_a * tiles_b;
+    }
+  }
+  __device__ bool next(Work& w) {
+    if (pos >= end) return false;
+    if (SWAP) {
+      w.ta = (int)(pos / k_blocks);
+      w.tb = 0;
+      w.kb0 = (int)(pos - (long long)w.ta * k_blocks);
+      const long long left = end - pos;
+      w.kb1 = (left < (long long)(k_blocks - w.kb0)) ? w.kb0 + (int)left : k_blocks;
+      pos += w.kb1 - w.kb0;
+    } else {
+      const int u = (int)pos;
+      const int group_size = GROUP_M * tiles_b;
+      const int group = u / group_size;
+      const int first = group * GROUP_M;
+      const int gm = min(GROUP_M, tiles_a - first);
+      const int r = u - group * group_size;
+      w.ta = first + r % gm;
+      w.tb = r / gm;
+      w.kb0 = 0;
+      w.kb1 = k_blocks;
+      pos += gridDim.x;
+    }
+    return true;
+  }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ------------------------------------------------------------------ the kernel
 template <bool SWAP, int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p,
-                        int k_blocks, int splitk, int tiles_a, int tiles_b, float* __restrict__ ws,
-                        int* __restrict__ counters) {
+                        int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
+                        int* __restrict__ flags) {
   using L = SmemLayout<SWAP, BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -202,12 +268,9 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 4) * 8);
-  volatile int* flag_smem = reinterpret_cast<volatile int*>(smem_gen + L::BAR_OFFSET + (2 * STAGES + 4) * 8 + 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int kbs = (k_blocks + splitk - 1) / splitk;   // k-blocks per split
-  const int total_units = SWAP ? tiles_a * splitk : tiles_a * tiles_b;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -235,42 +298,21 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  auto decode_unit = [&](int u, int& ta, int& tb, int& kb0, int& kb1, int& split) {
-    if (SWAP) {
-      ta = u / splitk;
-      split = u - ta * splitk;
-      tb = 0;
-      kb0 = split * kbs;
-      kb1 = min(kb0 + kbs, k_blocks);
-    } else {
-      const int group_size = GROUP_M * tiles_b;
-      const int group = u / group_size;
-      const int first = group * GROUP_M;
-      const int gm = min(GROUP_M, tiles_a - first);
-      const int r = u - group * group_size;
-      ta = first + r % gm;
-      tb = r / gm;
-      kb0 = 0;
-      kb1 = k_blocks;
-      split = 0;
-    }
-  };
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        int ta, tb, kb0, kb1, split;
-        decode_unit(u, ta, tb, kb0, kb1, split);
-        for (int kb = kb0; kb < kb1; ++kb) {
+      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+      Work w;
+      while (sched.next(w)) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
           mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, kb * BLOCK_K, ta * TILE_A, full_bar(stage));
-          tma_load_2d(sb, &tmB, kb * BLOCK_K, tb * BN, full_bar(stage));
+          tma_load_2d(sa, &tmA, kb * BLOCK_K, w.ta * TILE_A, full_bar(stage));
+          tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -286,13 +328,13 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-        int ta, tb, kb0, kb1, split;
-        decode_unit(u, ta, tb, kb0, kb1, split);
+      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+      Work w;
+      while (sched.next(w)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
@@ -301,7 +343,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
           }
           tcgen05_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
           if (++stage == STAGES) {
@@ -317,11 +359,12 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   } else if (warp >= EPI_WARP0) {
     // ===================== epilogue =====================
     const int ew = warp - EPI_WARP0;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const int et = threadIdx.x - EPI_WARP0 * 32;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < total_units; u += gridDim.x) {
-      int ta, tb, kb0, kb1, split;
-      decode_unit(u, ta, tb, kb0, kb1, split);
+    Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+    Work w;
+    while (sched.next(w)) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(ew * 32) << 16);
@@ -362,8 +405,8 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             uint4 q;
             const uint32_t addr = stg + r * 128 + ((ch ^ (r & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-            const int m = ta * TILE_A + ew * 32 + r;
-            const int n = tb * BN + c0 + ch * 8;
+            const int m = w.ta * TILE_A + ew * 32 + r;
+            const int n = w.tb * BN + c0 + ch * 8;
             if (m < p.M && n < p.N) {
               float f[8];
               unpack8(q, f);
@@ -375,72 +418,73 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       } else {
         // tile rows = output features (TMEM lanes), columns = tokens: transpose through smem / workspace
         const int nl = ew * 32 + lane;                     // feature inside the tile
-        const int ncol = ta * TILE_A + nl;
         float* stgf = reinterpret_cast<float*>(smem_gen + STAGES * L::STAGE_BYTES);
-        const int ldws = tiles_a * TILE_A;
+        const bool full = (w.kb0 == 0 && w.kb1 == k_blocks);
+        const bool owner = (w.kb0 == 0);                   // first k-piece: this CTA finishes the tile
+        float* slot = ws + (size_t)blockIdx.x * (BN * TILE_A);
         constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += CH) {
           uint32_t v[CH];
           if (CH == 32) tmem_ld32(taddr + c0, v); else tmem_ld16(taddr + c0, v);
           tmem_ld_wait();
-          if (splitk == 1) {
+          if (owner) {
 #pragma unroll
             for (int j = 0; j < CH; ++j) stgf[(c0 + j) * SWAP_LD + nl] = __uint_as_float(v[j]);
           } else {
 #pragma unroll
             for (int j = 0; j < CH; ++j)
-              if (c0 + j < p.M) ws[((size_t)split * BN + c0 + j) * ldws + ncol] = __uint_as_float(v[j]);
+              if (c0 + j < p.M) slot[(c0 + j) * TILE_A + nl] = __uint_as_float(v[j]);
           }
         }
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty_bar(acc));
-        bool do_reduce = true;
-        if (splitk > 1) {
+        if (!owner) {
+          // publish this CTA's piece
           __threadfence();
           epi_bar_sync();
-          if (threadIdx.x == EPI_WARP0 * 32) {
-            const int old = atomicAdd(&counters[ta], 1);
-            const int last = (old == splitk - 1);
-            if (last) counters[ta] = 0;                    // self-reset for the next GEMM call
-            *flag_smem = last;
+          if (et == 0) st_release_gpu(flags + blockIdx.x, 1);
+        } else {
+          // contributors are CTAs c+1, c+2, ... whose spans start inside this tile
+          const long long total = (long long)tiles_a * k_blocks;
+          const long long tile_end = (long long)(w.ta + 1) * k_blocks;
+          int last_c = blockIdx.x;
+          if (!full) {
+            while (last_c + 1 < (int)gridDim.x && total * (last_c + 1) / gridDim.x < tile_end) ++last_c;
+            if (et == 0) {
+              for (int c = blockIdx.x + 1; c <= last_c; ++c)
+                while (ld_acquire_gpu(flags + c) == 0) {
+                }
+            }
           }
           epi_bar_sync();
-          do_reduce = (*flag_smem != 0);
-          if (do_reduce) __threadfence();
-        } else {
-          epi_bar_sync();
-        }
-        if (do_reduce) {
-          const int et = threadIdx.x - EPI_WARP0 * 32;     // 0..127
           const int rows = min(BN, p.M);
           for (int vec = et; vec < rows * (TILE_A / 8); vec += 128) {
             const int m = vec / (TILE_A / 8);
             const int c8 = vec - m * (TILE_A / 8);
-            const int n = ta * TILE_A + c8 * 8;
+            const int n = w.ta * TILE_A + c8 * 8;
             if (n >= p.N) continue;
             float f[8];
-            if (splitk == 1) {
+            {
               const float4 a = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8);
               const float4 b = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8 + 4);
               f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) f[i] = 0.f;
-              for (int s = 0; s < splitk; ++s) {             // fixed order: deterministic
-                const float* src = ws + ((size_t)s * BN + m) * ldws + n;
-                const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
-                const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
-                f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
-              }
+            }
+            for (int c = blockIdx.x + 1; c <= last_c; ++c) {   // fixed k order: deterministic
+              const float* src = ws + (size_t)c * (BN * TILE_A) + m * TILE_A + c8 * 8;
+              const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
+              const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
+              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i]);
             epilogue_store8(p, m, n, f);
           }
+          epi_bar_sync();                                  // staging reuse; all pieces consumed
+          if (et == 0)
+            for (int c = blockIdx.x + 1; c <= last_c; ++c) flags[c] = 0;   // re-arm for the next launch
         }
-        epi_bar_sync();                                    // staging / flag reuse by the next unit
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
@@ -497,50 +541,48 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int K, int box_rows)
 struct Plan {
   bool swap;
   int bn;
-  int splitk;
+  int grid;      // CTAs
+  int streamk;   // SWAP: split tiles across CTAs at k-block granularity
   int tiles_a, tiles_b, k_blocks;
 };
 
 Plan make_plan(int M, int N, int K) {
   Plan pl;
+  const int sms = lia_sm_count();
   pl.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   pl.swap = (M <= 128);
-  pl.splitk = 1;
+  pl.streamk = 0;
   if (pl.swap) {
     pl.bn = M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128;
     pl.tiles_a = (N + TILE_A - 1) / TILE_A;
     pl.tiles_b = 1;
-    // split K so that (almost) every SM streams weights; keep >= 4 k-blocks per split
-    const int sms = lia_sm_count();
-    double best = -1.0;
-    const char* force = getenv("LIA_SPLITK");   // tuning/debug override
-    const int forced = force ? atoi(force) : 0;
-    for (int s = 1; s <= MAX_SPLITK; ++s) {
-      if (pl.k_blocks / s < 4 && s > 1) break;
-      const int kbs = (pl.k_blocks + s - 1) / s;
-      if ((s - 1) * kbs >= pl.k_blocks) continue;          // an empty split
-      const int units = pl.tiles_a * s;
-      const int waves = (units + sms - 1) / sms;
-      const double eff = (double)units / ((double)waves * sms) - 0.01 * (s - 1);   // mild penalty per extra split
-      if (eff > best) {
-        best = eff;
-        pl.splitk = s;
-      }
-    }
-    if (forced >= 1 && forced <= MAX_SPLITK && pl.k_blocks / forced >= 1) {
-      const int kbs = (pl.k_blocks + forced - 1) / forced;
-      if ((forced - 1) * kbs < pl.k_blocks) pl.splitk = forced;
-    }
+    // stream-K: every CTA streams the same number of k-blocks (>= 4 each)
+    const long long total = (long long)pl.tiles_a * pl.k_blocks;
+    long long g = total / 4;
+    if (g < 1) g = 1;
+    if (g > sms) g = sms;
+    pl.grid = (int)g;
+    pl.streamk = (total % pl.grid != 0 || pl.tiles_a % pl.grid != 0) ? 1 : 0;
+    const char* env = getenv("LIA_STREAMK");   // tuning/debug override: 0 = whole tiles per CTA
+    if (env && atoi(env) == 0) pl.streamk = 0;
+    if (!pl.streamk && pl.grid > pl.tiles_a) pl.grid = pl.tiles_a;
   } else {
     pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
     pl.tiles_a = (M + TILE_A - 1) / TILE_A;
     pl.tiles_b = (N + pl.bn - 1) / pl.bn;
+    const int units = pl.tiles_a * pl.tiles_b;
+    pl.grid = units < sms ? units : sms;
   }
   return pl;
 }
 
+size_t plan_workspace(const Plan& pl) {
+  if (!(pl.swap && pl.streamk)) return COUNTER_BYTES;
+  return COUNTER_BYTES + (size_t)pl.grid * pl.bn * TILE_A * sizeof(float);
+}
+
 template <bool SWAP, int BN, int STAGES>
-int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* counters,
+int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* flags,
            cudaStream_t stream) {
   using L = SmemLayout<SWAP, BN, STAGES>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
@@ -550,9 +592,7 @@ int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  const int units = SWAP ? pl.tiles_a * pl.splitk : pl.tiles_a * pl.tiles_b;
-  const int grid = units < lia_sm_count() ? units : lia_sm_count();
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.splitk, pl.tiles_a, pl.tiles_b, ws, counters);
+  kern<<<pl.grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.streamk, pl.tiles_a, pl.tiles_b, ws, flags);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
 }
@@ -561,10 +601,7 @@ int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 extern "C" size_t lia_gemm_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
-  const Plan pl = make_plan(M, N, K);
-  size_t bytes = COUNTER_BYTES;
-  if (pl.swap && pl.splitk > 1) bytes += (size_t)pl.splitk * pl.bn * pl.tiles_a * TILE_A * sizeof(float);
-  return bytes;
+  return plan_workspace(make_plan(M, N, K));
 }
 
 extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
@@ -600,13 +637,13 @@ extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, con
   }
   Plan pl = make_plan(M, N, K);
   float* ws = nullptr;
-  int* counters = nullptr;
-  if (pl.swap && pl.splitk > 1) {
-    const size_t need = COUNTER_BYTES + (size_t)pl.splitk * pl.bn * pl.tiles_a * TILE_A * sizeof(float);
-    if (workspace == nullptr || workspace_bytes < need || pl.tiles_a * (int)sizeof(int) > COUNTER_BYTES) {
-      pl.splitk = 1;   // no workspace: stream the weights with fewer CTAs rather than fail
+  int* flags = nullptr;
+  if (pl.swap && pl.streamk) {
+    if (workspace == nullptr || workspace_bytes < plan_workspace(pl) || pl.grid * (int)sizeof(int) > COUNTER_BYTES) {
+      pl.streamk = 0;   // no workspace: whole tiles per CTA (some SMs idle) rather than fail
+      if (pl.grid > pl.tiles_a) pl.grid = pl.tiles_a;
     } else {
-      counters = reinterpret_cast<int*>(workspace);
+      flags = reinterpret_cast<int*>(workspace);
       ws = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + COUNTER_BYTES);
     }
   }
@@ -616,15 +653,15 @@ extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, con
     if ((rc = make_tmap(&tmA, W, N, K, TILE_A)) != LIA_OK) return rc;
     if ((rc = make_tmap(&tmB, A, M, K, pl.bn)) != LIA_OK) return rc;
     switch (pl.bn) {
-      case 16: return launch<true, 16, 8>(pl, tmA, tmB, ep, ws, counters, stream);
-      case 32: return launch<true, 32, 8>(pl, tmA, tmB, ep, ws, counters, stream);
-      case 64: return launch<true, 64, 7>(pl, tmA, tmB, ep, ws, counters, stream);
-      default: return launch<true, 128, 4>(pl, tmA, tmB, ep, ws, counters, stream);
+      case 16: return launch<true, 16, 8>(pl, tmA, tmB, ep, ws, flags, stream);
+      case 32: return launch<true, 32, 8>(pl, tmA, tmB, ep, ws, flags, stream);
+      case 64: return launch<true, 64, 7>(pl, tmA, tmB, ep, ws, flags, stream);
+      default: return launch<true, 128, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     }
   } else {
     if ((rc = make_tmap(&tmA, A, M, K, TILE_A)) != LIA_OK) return rc;
     if ((rc = make_tmap(&tmB, W, N, K, pl.bn)) != LIA_OK) return rc;
-    if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, counters, stream);
-    return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, counters, stream);
+    if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, flags, stream);
+    return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, flags, stream);
   }
 }

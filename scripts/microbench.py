@@ -30,7 +30,7 @@ def bench_gemm(M, N, K, epi, nbuf=4, label=""):
     ms = timeit(lambda i: ops.gemm(a, ws_[i % nbuf], bias, out=out, epilogue=epi, residual=res, workspace=wsp))
     byts = 2.0 * N * K + 2.0 * M * K + 2.0 * M * N
     fl = 2.0 * M * N * K
-    print(f"gemm {label:8s} M={M:6d} N={N:6d} K={K:6d} epi={epi} splitk_env={os.environ.get('LIA_SPLITK','-')}: {ms*1e3:9.1f} us  {byts/ms/1e6:8.1f} GB/s ({byts/ms/1e6/HBM*100:5.1f}% HBM)  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
+    print(f"gemm {label:8s} M={M:6d} N={N:6d} K={K:6d} epi={epi} streamk_env={os.environ.get('LIA_STREAMK','-')}: {ms*1e3:9.1f} us  {byts/ms/1e6:8.1f} GB/s ({byts/ms/1e6/HBM*100:5.1f}% HBM)  {fl/ms/1e9:8.1f} TFLOP/s", flush=True)
     return ms
 
 def bench_attn(T, nbuf=3):
