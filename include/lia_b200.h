@@ -108,6 +108,12 @@ int lia_attn_decode_bf16(const void* q, const void* k_cache, const void* v_cache
                          int d, int cache_batch, int b0, int splits, void* workspace, size_t workspace_bytes,
                          lia_stream_t stream);
 
+/* Stand-alone Q scaling + KV-cache append for callers that hold separate q/k/v [B,S,hq] (the
+ * IndirectAccessKVCache operator face, llm/modules/mha_fusion.py:503-560); the model path fuses this
+ * into the QKV GEMM epilogue.  q_out = bf16(q*q_scale); caches as in LiaQkvArgs (A:456-491). */
+int lia_kv_append_bf16(const void* q, const void* k, const void* v, void* q_out, void* k_cache, void* v_cache, int B,
+                       int S, int hq, int pos0, int cache_batch, int b0, float q_scale, lia_stream_t stream);
+
 /* hidden[b,s,:] = embed_tokens[ids[b,s]] + embed_positions[past_len + s + 2]  (M:1107-1142 with
  * an all-ones attention mask, M:368-378).  ids int64 [B,S]. */
 int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,

@@ -38,6 +38,8 @@ _PROTOTYPES = {
     "lia_attn_decode_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "lia_attn_decode_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                      c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "lia_kv_append_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                   c_int, c_int, c_float, c_void_p]),
     "lia_embed_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
     "lia_argmax_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

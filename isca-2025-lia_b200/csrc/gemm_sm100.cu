@@ -655,7 +655,7 @@ extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, con
     switch (pl.bn) {
       case 16: return launch<true, 16, 8>(pl, tmA, tmB, ep, ws, flags, stream);
       case 32: return launch<true, 32, 8>(pl, tmA, tmB, ep, ws, flags, stream);
-      case 64: return launch<true, 64, 7>(pl, tmA, tmB, ep, ws, flags, stream);
+      case 64: return launch<true, 64, 8>(pl, tmA, tmB, ep, ws, flags, stream);
       default: return launch<true, 128, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     }
   } else {

@@ -96,7 +96,45 @@ __global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restric
   }
 }
 
+// q_out = bf16(q * scale); k_cache[pos0+s, b0+b] = k; v_cache[pos0+s, b0+b] = v  (attentions.py:456-491)
+// for callers that computed q/k/v themselves (the IndirectAccessKVCache operator face); the model
+// path fuses this into the QKV GEMM epilogue instead.
+__global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+                                                        const bf16* __restrict__ v, bf16* __restrict__ q_out,
+                                                        bf16* __restrict__ kc, bf16* __restrict__ vc, int S, int hq,
+                                                        int pos0, int cache_batch, int b0, float scale) {
+  const int row = blockIdx.x;          // b*S + s
+  const int b = row / S;
+  const int s = row - b * S;
+  const size_t src = (size_t)row * hq;
+  const size_t dst = ((size_t)(pos0 + s) * cache_batch + b0 + b) * hq;
+  for (int i = threadIdx.x * 8; i < hq; i += 128 * 8) {
+    float f[8];
+    unpack8(ldg_stream(q + src + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= scale;
+    *reinterpret_cast<uint4*>(q_out + src + i) = pack8(f);
+    *reinterpret_cast<uint4*>(kc + dst + i) = ldg_stream(k + src + i);
+    *reinterpret_cast<uint4*>(vc + dst + i) = ldg_stream(v + src + i);
+  }
+}
+
 }  // namespace
+
+extern "C" int lia_kv_append_bf16(const void* q, const void* k, const void* v, void* q_out, void* k_cache, void* v_cache,
+                                  int B, int S, int hq, int pos0, int cache_batch, int b0, float q_scale,
+                                  lia_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  LIA_CHECK_ARG(q && k && v && q_out && k_cache && v_cache, "lia_kv_append_bf16: null pointer");
+  LIA_CHECK_ARG(B > 0 && S > 0 && hq > 0 && hq % 8 == 0, "lia_kv_append_bf16: bad shape");
+  LIA_CHECK_ARG(pos0 >= 0 && b0 >= 0 && b0 + B <= cache_batch, "lia_kv_append_bf16: batch window outside the cache");
+  kv_append_kernel<<<B * S, 128, 0, stream>>>(reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k),
+                                              reinterpret_cast<const bf16*>(v), reinterpret_cast<bf16*>(q_out),
+                                              reinterpret_cast<bf16*>(k_cache), reinterpret_cast<bf16*>(v_cache), S, hq, pos0,
+                                              cache_batch, b0, q_scale);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}
 
 extern "C" int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
                               int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream_) {

@@ -89,6 +89,19 @@ def qkv_args(q_out, k_cache, v_cache, S, pos0, b0, scale):
                       float(scale))
 
 
+def kv_append(q, k, v, k_cache, v_cache, pos0, b0, scale, q_out=None):
+    """q_out = q*scale; append k/v rows [B,S,H,d] to the time-major cache (attentions.py:456-491)."""
+    _req(q, "q"); _req(k, "k"); _req(v, "v"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
+    B, S = q.shape[0], q.shape[1]
+    hq = k_cache.shape[2] * k_cache.shape[3]
+    if q_out is None:
+        q_out = torch.empty_like(q)
+    check(_lib.load().lia_kv_append_bf16(_p(q), _p(k), _p(v), _p(q_out), _p(k_cache), _p(v_cache), B, S, hq, pos0,
+                                         k_cache.shape[1], b0, float(scale), _stream()), "lia_kv_append_bf16")
+    count_launches()
+    return q_out
+
+
 def attn_prefill(q, k_cache, v_cache, B, S, b0=0, out=None):
     """Causal attention over rows [0,S) of the cache (attentions.py:444-449, 493-536)."""
     _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")

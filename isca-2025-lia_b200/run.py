@@ -1,0 +1,126 @@
+"""Command line of the reference's benchmark driver, on the B200 build.
+
+Same flags as examples/cpu/inference/python/llm/run.py:169-215 and
+single_instance/run_generation.py:59-118, same printed summary lines
+(run_generation.py:330-354) -- plus tokens/s and roofline fractions, which the reference
+never prints.  Prompts are synthetic token ids (no tokenizer / prompt.json offline):
+``randint(3, vocab)`` of length --input-tokens, identical for every batch row as in
+run_generation.py:285.
+
+Policy mapping: 0/2/3/4 run everything on the GPU (non-resident layers streamed from pinned
+host memory); 1 (the reference's default: full-CPU IPEX/AMX) is refused with a pointer to
+``bench.py --impl reference``.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+
+def build_parser():
+    p = argparse.ArgumentParser("Generation script (bf16 path, B200 build)")
+    p.add_argument("-m", "--model-id", "--model-name-or-path", dest="model_id", type=str, default="facebook/opt-30b")
+    p.add_argument("--dtype", type=str, choices=["float32", "bfloat16"], default="bfloat16")
+    p.add_argument("--input-tokens", default="32", type=str)
+    p.add_argument("--max-new-tokens", default=32, type=int)
+    p.add_argument("--prompt", default=None, type=str)
+    p.add_argument("--greedy", action="store_true")
+    p.add_argument("--ipex", action="store_true")
+    p.add_argument("--deployment-mode", action="store_true")
+    p.add_argument("--profile", action="store_true")
+    p.add_argument("--benchmark", action="store_true")
+    p.add_argument("--num-iter", default=100, type=int)
+    p.add_argument("--num-warmup", default=10, type=int)
+    p.add_argument("--batch-size", default=1, type=int)
+    p.add_argument("--token-latency", action="store_true")
+    p.add_argument("--prefill-policy", default=1, type=int)
+    p.add_argument("--decoding-policy", default=1, type=int)
+    p.add_argument("--no-overlap", action="store_true")
+    p.add_argument("--pin-weight", action="store_true")
+    p.add_argument("--gpu-percentage", default=0, type=int)
+    p.add_argument("--num-minibatch", default=1, type=int)
+    p.add_argument("--enable-cxl", action="store_true")
+    # additions of this build
+    p.add_argument("--tp", default=0, type=int, help="tensor-parallel world size (default: WORLD_SIZE)")
+    p.add_argument("--dummy-weights", action="store_true", help="U[0,1) weights as utils/opt-weight-gen.py")
+    p.add_argument("--num-layers", default=0, type=int, help="override depth (debug)")
+    p.add_argument("--seed", default=0, type=int)
+    return p
+
+
+def main(argv=None):
+    args = build_parser().parse_args(argv)
+    print(args)
+    if args.dtype != "bfloat16":
+        print("error: only --dtype bfloat16 is implemented on the B200 path", file=sys.stderr)
+        return 2
+    if args.prefill_policy == 1 or args.decoding_policy == 1:
+        print("error: policy 1 is the reference's full-CPU (IPEX/AMX) path, which this build does not contain; "
+              "use --prefill-policy 0 --decoding-policy 0 (all-GPU, streamed weights) or time the CPU baseline with "
+              "`python bench.py --impl reference`.", file=sys.stderr)
+        return 2
+    import torch
+    import lia_b200
+    from lia_b200 import tp
+    from lia_b200.modeling_opt import get_config
+    rank, world = tp.init_from_env()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    cfg = get_config(args.model_id)
+    if args.num_layers:
+        cfg.num_hidden_layers = args.num_layers
+    cfg.token_latency = bool(args.token_latency)
+    S = int(args.input_tokens)
+    cfg.text_max_length = S + args.max_new_tokens                     # run_generation.py:149
+    model = lia_b200.OPTForCausalLM(cfg, torch.device("cuda", local), tp_rank=rank, tp_world=world)
+    model.init_weights(seed=args.seed, kind="dummy" if args.dummy_weights else "normal", gpu_percentage=args.gpu_percentage)
+    g = torch.Generator().manual_seed(1234)
+    prompt = torch.randint(3, cfg.vocab_size, (1, S), generator=g)
+    input_ids = prompt.expand(args.batch_size, S).contiguous().pin_memory()       # run_generation.py:285
+    generate_kwargs = dict(do_sample=False, temperature=0.9, num_beams=1 if args.greedy else 1,
+                           max_new_tokens=args.max_new_tokens, min_new_tokens=args.max_new_tokens,
+                           prefill_policy=args.prefill_policy, decoding_policy=args.decoding_policy,
+                           no_overlap=args.no_overlap, pin_weight=args.pin_weight, gpu_percentage=args.gpu_percentage,
+                           num_minibatch=args.num_minibatch, enable_cxl=args.enable_cxl)      # run_generation.py:179-182
+    total_time, total_list = 0.0, []
+    num_iter, num_warmup = args.num_iter, args.num_warmup
+    for i in range(num_iter):
+        tic = time.time()
+        output = model.generate(input_ids, **generate_kwargs)
+        gen_ids = output[0] if args.token_latency else output
+        toc = time.time()
+        total_new_tokens = [int(o.shape[0]) - S for o in gen_ids]
+        if rank == 0:
+            print(total_new_tokens[:4], flush=True)
+            print("Iteration: %d, Time: %.6f sec" % (i, toc - tic), flush=True)
+        if i >= num_warmup:
+            total_time += toc - tic
+            if args.token_latency:
+                total_list.append(output[1])
+    if rank != 0:
+        return 0
+    print("\n", "-" * 10, "Summary:", "-" * 10)
+    latency = total_time / max(1, num_iter - num_warmup)
+    print("Inference latency: %.3f sec." % latency)
+    if args.token_latency and total_list:
+        import numpy as np
+        from itertools import chain
+        first_latency = np.mean([x[0] for x in total_list])
+        average_2n = sorted(chain(*[x[1:] for x in total_list]))
+        print("First token average latency: %.3f sec." % first_latency)
+        if average_2n:
+            print("Average 2... latency: %.3f sec." % np.mean(average_2n))
+            print("P90 2... latency: %.3f sec." % average_2n[int(len(average_2n) * 0.9)])
+            print("P99 2... latency: %.3f sec." % average_2n[int(len(average_2n) * 0.99)])
+    print("Throughput: %.1f tokens/sec (batch %d x %d new tokens)" % (args.batch_size * args.max_new_tokens / latency,
+                                                                     args.batch_size, args.max_new_tokens))
+    st = model.model.decoder.streamer
+    if st is not None:
+        s = st.stats()
+        print("Streamed weights: %.2f GB at %.1f GB/s (pinned host -> HBM)" % (s["bytes"] / 1e9, s["gbps"]))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

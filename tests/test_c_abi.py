@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads without a GPU and exports
+every symbol include/lia_b200.h declares; the ctypes binding covers all of them; argument
+validation fails loudly.  No compute calls."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as g
+    g.build()
+    import lia_b200
+    from lia_b200 import _lib
+    return _lib
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "lia_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lia_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported_and_bound(built):
+    names = header_functions()
+    assert len(names) >= 20
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lia_b200.h but not exported"
+        assert n in built.EXPORTS, f"{n} has no ctypes prototype in _lib.py"
+    assert set(built.EXPORTS) == set(names)
+
+
+def test_abi_version_and_struct_layout(built):
+    lib = built.load()
+    assert lib.lia_abi_version() == built.ABI_VERSION == 1
+    # LiaQkvArgs: 3 pointers + 5 int32 + 1 float, natural alignment
+    assert ctypes.sizeof(built.LiaQkvArgs) == 48
+    assert built.LiaQkvArgs.hq.offset == 24 and built.LiaQkvArgs.q_scale.offset == 44
+
+
+def test_argument_errors_are_reported_not_crashed(built):
+    lib = built.load()
+    rc = lib.lia_gemm_bf16(None, None, None, None, None, 4, 16, 12, 0, None, None, 0, None)
+    assert rc == -1 and "multiples of 8" in built.last_error()
+    rc = lib.lia_layernorm_bf16(None, None, None, None, 1, 64, 1e-5, None)
+    assert rc == -1 and "null" in built.last_error()
+    rc = lib.lia_attn_decode_bf16(1, 1, 1, 1, 2, 2, 8, 96, 2, 0, 0, None, 0, None)
+    assert rc == -1 and "64 or 128" in built.last_error()
+    with pytest.raises(built.LiaError):
+        built.check(rc, "lia_attn_decode_bf16")
+    assert lib.lia_gemm_workspace_bytes(64, 7168, 7168) > 16384
+    assert lib.lia_attn_decode_workspace_bytes(64, 56, 128, 0) == 64 * 56 * 32 * 130 * 4
+
+
+def test_missing_library_is_fatal(built, monkeypatch):
+    monkeypatch.setattr(built, "_lib", None)
+    monkeypatch.setattr(built, "LIB_PATH", "/nonexistent/libliab200.so")
+    with pytest.raises(built.LiaError):
+        built.load()
+
+
+def test_ops_refuse_cpu_tensors(built):
+    import torch
+    from lia_b200 import ops
+    with pytest.raises(built.LiaError):
+        ops.layernorm(torch.zeros(2, 64, dtype=torch.bfloat16), torch.ones(64, dtype=torch.bfloat16),
+                      torch.zeros(64, dtype=torch.bfloat16))
+    with pytest.raises(built.LiaError):
+        ops.gemm(torch.zeros(2, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16), None)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "isca-2025-lia_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", ""), f"{f} references the oracle"

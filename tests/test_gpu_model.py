@@ -228,3 +228,43 @@ def test_policy1_is_refused(lia):
     m = lia.OPTForCausalLM(cfg, "cuda").init_weights()
     with pytest.raises(NotImplementedError):
         m.generate(torch.randint(3, 64, (1, 4)), max_new_tokens=2, prefill_policy=1, decoding_policy=1)
+
+
+def test_operator_registry_cuda_table(lia):
+    """The reference's op-level plugin API (ipex.llm.modules) with a "cuda" table: same call
+    signatures, each backed by one C-ABI entry point."""
+    from lia_b200 import llm_modules as lm
+    assert set(lm.fusion_modules["cuda"]) == {lm.IPEXCustomOpType.LINEAR_RELU, lm.IPEXCustomOpType.LINEAR_ADD,
+                                              lm.IPEXCustomOpType.FAST_LAYERNORM, lm.IPEXCustomOpType.INDIRECTACCESS_KVCACHE}
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(256, 512).to(BF16)
+    x = torch.randn(1, 4, 256).to(BF16).cuda()
+    y = torch.randn(1, 4, 512).to(BF16).cuda()
+    ref = torch.nn.functional.linear(x.float(), lin.weight.float().cuda(), lin.bias.float().cuda())
+    # tests/cpu/test_ipex_llm_module.py:166,200 compare against eager relu(linear(x)) / linear(x)+y
+    assert rel_err(lm.LinearRelu(lin)(x), torch.relu(ref)) <= REL_TOL
+    assert rel_err(lm.LinearAdd(lin)(x, y), ref + y.float()) <= REL_TOL
+    ln = torch.nn.LayerNorm(256).to(BF16)
+    with torch.no_grad():
+        ln.weight.normal_(1, 0.1); ln.bias.normal_(0, 0.1)
+    ref_ln = torch.nn.functional.layer_norm(x.float(), (256,), ln.weight.float().cuda(), ln.bias.float().cuda(), 1e-5)
+    assert rel_err(lm.FastLayerNorm(256, 1e-5, ln.weight, ln.bias)(x), ref_ln) <= REL_TOL
+    assert rel_err(lm.FastLayerNorm.apply(x, 256, ln.weight.cuda(), ln.bias.cuda(), 1e-5), ref_ln) <= REL_TOL
+    # IndirectAccessKVCache: first token then two next tokens vs naive cat-KV attention (tests/cpu/test_masked_mha.py)
+    B, S, H, d = 2, 9, 4, 64
+    q, k, v = (torch.randn(B, S, H, d).to(BF16).cuda() for _ in range(3))
+    cache = lm.IndirectAccessKVCache(text_max_length=32)
+    out, _, past = cache(q, k, v, d ** 0.5, None, None, None)
+    def naive(q_, k_, v_, causal):
+        s = (q_.float().permute(0, 2, 1, 3) @ k_.float().permute(0, 2, 3, 1)) / d ** 0.5
+        if causal:
+            s = s.masked_fill(torch.triu(torch.ones(s.shape[-2:], dtype=torch.bool, device="cuda"), 1), float("-inf"))
+        return (torch.softmax(s, -1) @ v_.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    assert past[0].shape[2] == S and rel_err(out, naive(q, k, v, True)) <= 2e-2      # bf16 prec of test_masked_mha.py:277-280
+    ks, vs = k, v
+    for step in range(2):
+        q1, k1, v1 = (torch.randn(B, 1, H, d).to(BF16).cuda() for _ in range(3))
+        out, _, past = cache(q1, k1, v1, d ** 0.5, past, None, None)
+        ks, vs = torch.cat([ks, k1], 1), torch.cat([vs, v1], 1)
+        assert past[0].shape[2] == S + step + 1 and rel_err(out, naive(q1, ks, vs, False)) <= 2e-2
+    assert torch.equal(past[1][:S + 2].permute(1, 0, 2, 3), ks)                      # cache contents, time-major

@@ -1,0 +1,137 @@
+"""Host-side logic that needs no GPU: slab layout, TP sharding, the stream-K partition the decode
+GEMM uses, config table, CLI flags, policy mapping, the CPU-baseline arm of bench.py."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lia_b200  # noqa: E402
+from lia_b200 import weights  # noqa: E402
+from lia_b200.modeling_opt import OPT_CONFIGS, _check_policy, get_config  # noqa: E402
+from oracle import opt_ref  # noqa: E402
+
+
+def test_config_table_matches_survey():
+    dims = {"opt-1.3b": (24, 2048, 32, 8192), "opt-30b": (48, 7168, 56, 28672), "opt-66b": (64, 9216, 72, 36864),
+            "opt-175b": (96, 12288, 96, 49152)}
+    for k, (L, h, H, f) in dims.items():
+        c = get_config("facebook/" + k)
+        assert (c.num_hidden_layers, c.hidden_size, c.num_attention_heads, c.ffn_dim) == (L, h, H, f)
+        assert c.vocab_size == 50272 and c.max_position_embeddings == 2048 and c.head_dim in (64, 128)
+        lay = weights.LayerLayout(h, f)
+        assert lay.nbytes == 2 * (12 * h * h + 13 * h)           # W_l of SURVEY.md 8d
+    c = get_config("opt-30b")
+    c.num_hidden_layers = 2
+    assert OPT_CONFIGS["opt-30b"].num_hidden_layers == 48        # get_config returns a copy
+
+
+@pytest.mark.parametrize("world", [1, 2, 4])
+def test_slab_pack_and_tp_sharding(world):
+    h, f = 256, 1024
+    w = weights.random_layer(h, f, seed=3, bias_std=0.05, ln_std=0.1)
+    assert torch.equal(w["q_w"], weights.random_layer(h, f, seed=3, bias_std=0.05, ln_std=0.1)["q_w"])
+    lay = weights.LayerLayout(h, f, world)
+    for off, n in lay.offsets.values():
+        assert off % 8 == 0 and n % 8 == 0                        # 16-byte aligned tensors
+    x = torch.randn(5, h).to(torch.bfloat16)
+    full = torch.relu(x.float() @ w["fc1_w"].float().t() + w["fc1_b"].float()) @ w["fc2_w"].float().t() + w["fc2_b"].float()
+    total = 0
+    for r in range(world):
+        v = lay.views(weights.pack_layer(w, lay, r))
+        ref = opt_ref.shard_layer(w, 4, r, world)                  # oracle's restatement of tensor_parallel.py
+        hq = h // world
+        assert torch.equal(v["qkv_w"][:hq], ref["q_w"]) and torch.equal(v["qkv_w"][2 * hq:], ref["v_w"])
+        assert torch.equal(v["o_w"], ref["o_w"]) and torch.equal(v["fc1_w"], ref["fc1_w"]) and torch.equal(v["fc2_w"], ref["fc2_w"])
+        assert torch.equal(v["qkv_b"][hq:2 * hq], ref["k_b"])
+        # row-parallel bias is divided by the world size (tensor_parallel.py:134)
+        assert torch.allclose(v["fc2_b"].float() * world, w["fc2_b"].float(), atol=1e-2)
+        total = total + torch.relu(x.float() @ v["fc1_w"].float().t() + v["fc1_b"].float()) @ v["fc2_w"].float().t() + v["fc2_b"].float()
+    assert torch.allclose(total, full, atol=2e-2, rtol=2e-2)
+
+
+def streamk_spans(tiles, k_blocks, grid):
+    """Python restatement of Sched<SWAP> in csrc/gemm_sm100.cu."""
+    total = tiles * k_blocks
+    out = []
+    for c in range(grid):
+        pos, end = total * c // grid, total * (c + 1) // grid
+        segs = []
+        while pos < end:
+            t = pos // k_blocks
+            kb0 = pos - t * k_blocks
+            kb1 = min(k_blocks, kb0 + (end - pos))
+            segs.append((t, kb0, kb1))
+            pos += kb1 - kb0
+        out.append(segs)
+    return out
+
+
+@pytest.mark.parametrize("tiles,k_blocks,grid", [(56, 112, 148), (168, 112, 148), (224, 112, 148), (56, 448, 148),
+                                                 (393, 112, 148), (1, 2, 1), (3, 5, 3), (2, 1, 1), (7, 33, 148 // 4)])
+def test_streamk_partition_properties(tiles, k_blocks, grid):
+    spans = streamk_spans(tiles, k_blocks, grid)
+    cover = {}
+    for c, segs in enumerate(spans):
+        non_owner = [s for s in segs if s[1] > 0]
+        partial_owner = [s for s in segs if s[1] == 0 and s[2] < k_blocks]
+        assert len(non_owner) <= 1 and len(partial_owner) <= 1           # one workspace slot per CTA suffices
+        if non_owner:
+            assert segs[0] == non_owner[0]                               # published first: the owner never deadlocks
+        if partial_owner:
+            assert segs[-1] == partial_owner[0]
+        for (t, a, b) in segs:
+            for kb in range(a, b):
+                assert (t, kb) not in cover
+                cover[(t, kb)] = c
+    assert len(cover) == tiles * k_blocks                                # every k-block exactly once
+    sizes = [sum(b - a for _, a, b in segs) for segs in spans]
+    assert max(sizes) - min(sizes) <= 1                                  # every SM streams the same bytes
+    # the owner of a split tile finds its contributors as the consecutive CTAs c+1.. (kernel's loop)
+    for c, segs in enumerate(spans):
+        for (t, a, b) in segs:
+            if a == 0 and b < k_blocks:
+                last = c
+                while last + 1 < grid and (tiles * k_blocks) * (last + 1) // grid < (t + 1) * k_blocks:
+                    last += 1
+                contributors = sorted({cover[(t, kb)] for kb in range(b, k_blocks)})
+                assert contributors == list(range(c + 1, last + 1))
+
+
+def test_policy_mapping():
+    for p in (0, 2, 3, 4):
+        assert _check_policy(p, "prefill_policy") == p
+    assert _check_policy(None, "x") == 3
+    with pytest.raises(NotImplementedError):
+        _check_policy(1, "decoding_policy")
+    with pytest.raises(ValueError):
+        _check_policy(7, "decoding_policy")
+
+
+def test_cli_has_every_reference_flag():
+    from lia_b200.run import build_parser, main
+    flags = {a for act in build_parser()._actions for a in act.option_strings}
+    # run.py:169-215 / run_generation.py:59-118
+    for f in ["-m", "--dtype", "--ipex", "--benchmark", "--input-tokens", "--max-new-tokens", "--batch-size", "--num-iter",
+              "--num-warmup", "--greedy", "--token-latency", "--profile", "--prefill-policy", "--decoding-policy",
+              "--no-overlap", "--pin-weight", "--gpu-percentage", "--num-minibatch", "--enable-cxl"]:
+        assert f in flags, f
+    a = build_parser().parse_args([])
+    assert (a.prefill_policy, a.decoding_policy, a.gpu_percentage, a.num_minibatch, a.max_new_tokens, a.num_iter,
+            a.num_warmup) == (1, 1, 0, 1, 32, 100, 10)                    # reference defaults
+    assert main(["-m", "facebook/opt-1.3b"]) == 2                        # default policy 1/1 = CPU path: refused
+
+
+def test_bench_reference_arm_contract():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "opt-125m",
+                          "--batch-size", "2", "--input-tokens", "16", "--max-new-tokens", "4", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
