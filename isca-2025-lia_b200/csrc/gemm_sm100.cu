@@ -26,6 +26,7 @@
 #include <cuda.h>
 
 #include <stdlib.h>
+#include <string.h>
 
 #include <mutex>
 
@@ -136,11 +137,12 @@ __host__ __device__ constexpr uint32_t make_idesc(int umma_m, int umma_n) {
 }
 
 // ------------------------------------------------------------------ epilogue on 8 consecutive columns
-// v[] holds r1 = bf16(acc) (as floats).  Rounding points follow SURVEY.md A.2.
-__device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n, float* v) {
+// v[] holds r1 = bf16(acc) (as floats).  Rounding points follow SURVEY.md A.2.  The loads the
+// epilogue needs (bias, residual) are split from the arithmetic so that callers can issue them
+// early -- they do not depend on the accumulator.
+__device__ __forceinline__ void epilogue_finish8(const EpiParams& p, int m, int n, float* v, const float* b,
+                                                 const uint4& res) {
   if (p.bias != nullptr) {
-    float b[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = bf16r(v[i] + b[i]);
   }
@@ -152,7 +154,7 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n
     *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
   } else if (p.mode == LIA_EPI_BIAS_RESIDUAL) {
     float r[8];
-    unpack8(ldg_stream(p.residual + (size_t)m * p.N + n), r);
+    unpack8(res, r);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = r[i] + v[i];
     *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
@@ -164,13 +166,26 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n
       for (int i = 0; i < 8; ++i) v[i] = v[i] * p.q_scale;
       *reinterpret_cast<uint4*>(p.q_out + (size_t)m * p.hq + c) = pack8(v);
     } else {
-      const int b = m / p.S;
-      const int s = m - b * p.S;
+      const int bb = m / p.S;
+      const int ss = m - bb * p.S;
       bf16* cache = (which == 1) ? p.k_cache : p.v_cache;
-      const size_t row = (size_t)(p.pos0 + s) * p.cache_batch + p.b0 + b;
+      const size_t row = (size_t)(p.pos0 + ss) * p.cache_batch + p.b0 + bb;
       *reinterpret_cast<uint4*>(cache + row * p.hq + c) = pack8(v);
     }
   }
+}
+__device__ __forceinline__ void epilogue_load_bias8(const EpiParams& p, int n, float* b) {
+  if (p.bias != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
+}
+__device__ __forceinline__ uint4 epilogue_load_residual8(const EpiParams& p, int m, int n) {
+  if (p.mode == LIA_EPI_BIAS_RESIDUAL) return ldg_stream(p.residual + (size_t)m * p.N + n);
+  return make_uint4(0, 0, 0, 0);
+}
+__device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n, float* v) {
+  float b[8];
+  epilogue_load_bias8(p, n, b);
+  const uint4 res = epilogue_load_residual8(p, m, n);
+  epilogue_finish8(p, m, n, v, b, res);
 }
 
 template <bool SWAP, int BN, int STAGES>
@@ -252,12 +267,21 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// optional per-CTA timeline (LIA_GEMM_TRACE=1): 8 globaltimer stamps per CTA in mapped host memory
+__device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    trace[blockIdx.x * 8 + i] = t;
+  }
+}
+
 // ------------------------------------------------------------------ the kernel
 template <bool SWAP, int BN, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
-                        int* __restrict__ flags) {
+                        int* __restrict__ flags, unsigned long long* __restrict__ trace) {
   using L = SmemLayout<SWAP, BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -271,6 +295,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) stamp(trace, 0);
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -297,12 +322,14 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  if (threadIdx.x == 0) stamp(trace, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      bool first_issue = true;
       Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
       Work w;
       while (sched.next(w)) {
@@ -313,6 +340,10 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
           tma_load_2d(sa, &tmA, kb * BLOCK_K, w.ta * TILE_A, full_bar(stage));
           tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));
+          if (first_issue) {
+            stamp(trace, 2);
+            first_issue = false;
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
@@ -328,6 +359,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      bool first_full = true;
       Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
       Work w;
       while (sched.next(w)) {
@@ -336,6 +368,10 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (first_full) {
+            stamp(trace, 3);
+            first_full = false;
+          }
           tcgen05_fence_after();
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint64_t da = make_smem_desc(sa);
@@ -352,6 +388,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           }
         }
         tcgen05_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        stamp(trace, 4);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -365,7 +402,25 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
     Work w;
     while (sched.next(w)) {
+      // SWAP: this thread finishes columns [n_col, n_col+8) of rows m0, m0+8, ... -- fetch what the
+      // epilogue needs besides the accumulator (bias, residual) BEFORE waiting for the MMAs
+      constexpr int ITERS = SWAP ? BN / 8 : 1;
+      const int c8 = et & 15, m0 = et >> 4;
+      const int rows = min(BN, p.M);
+      const int n_col = w.ta * TILE_A + c8 * 8;
+      const bool n_ok = SWAP && n_col < p.N;
+      float biasf[8];
+      uint4 resv[ITERS];
+      if (SWAP && w.kb0 == 0 && n_ok) {
+        epilogue_load_bias8(p, n_col, biasf);
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+          const int m = m0 + it * 8;
+          resv[it] = (m < rows) ? epilogue_load_residual8(p, m, n_col) : make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (et == 0) stamp(trace, 5);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(ew * 32) << 16);
 
@@ -459,27 +514,51 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             }
           }
           epi_bar_sync();
-          const int rows = min(BN, p.M);
-          for (int vec = et; vec < rows * (TILE_A / 8); vec += 128) {
-            const int m = vec / (TILE_A / 8);
-            const int c8 = vec - m * (TILE_A / 8);
-            const int n = w.ta * TILE_A + c8 * 8;
-            if (n >= p.N) continue;
-            float f[8];
-            {
-              const float4 a = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8);
-              const float4 b = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8 + 4);
-              f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-            }
-            for (int c = blockIdx.x + 1; c <= last_c; ++c) {   // fixed k order: deterministic
-              const float* src = ws + (size_t)c * (BN * TILE_A) + m * TILE_A + c8 * 8;
-              const float4 a = __ldcg(reinterpret_cast<const float4*>(src));
-              const float4 b = __ldcg(reinterpret_cast<const float4*>(src + 4));
-              f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
-            }
+          if (et == 0) stamp(trace, 6);
+          // thread -> 8 fixed columns (c8) and rows m0, m0+8, ...: ROWS_PER_BATCH rows at a time so that
+          // the loads of a batch (own sums from smem, pieces from L2) are all in flight together
+          if (n_ok) {
+            constexpr int RB = ITERS < 4 ? ITERS : 4;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i]);
-            epilogue_store8(p, m, n, f);
+            for (int it0 = 0; it0 < ITERS; it0 += RB) {
+              float f[RB][8];
+#pragma unroll
+              for (int j = 0; j < RB; ++j) {
+                const int m = m0 + (it0 + j) * 8;
+                const float4 a = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8);
+                const float4 b = *reinterpret_cast<const float4*>(stgf + m * SWAP_LD + c8 * 8 + 4);
+                f[j][0] = a.x; f[j][1] = a.y; f[j][2] = a.z; f[j][3] = a.w;
+                f[j][4] = b.x; f[j][5] = b.y; f[j][6] = b.z; f[j][7] = b.w;
+              }
+              for (int c = blockIdx.x + 1; c <= last_c; ++c) {   // fixed k order: deterministic
+                float4 pa[RB], pb[RB];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                  const int m = m0 + (it0 + j) * 8;
+                  const float* src = ws + (size_t)c * (BN * TILE_A) + m * TILE_A + c8 * 8;
+                  if (m < rows) {
+                    pa[j] = __ldcg(reinterpret_cast<const float4*>(src));
+                    pb[j] = __ldcg(reinterpret_cast<const float4*>(src + 4));
+                  } else {
+                    pa[j] = pb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+                }
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
+                  f[j][0] += pa[j].x; f[j][1] += pa[j].y; f[j][2] += pa[j].z; f[j][3] += pa[j].w;
+                  f[j][4] += pb[j].x; f[j][5] += pb[j].y; f[j][6] += pb[j].z; f[j][7] += pb[j].w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < RB; ++j) {
+                const int m = m0 + (it0 + j) * 8;
+                if (m < rows) {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[j][i] = bf16r(f[j][i]);
+                  epilogue_finish8(p, m, n_col, f[j], biasf, resv[it0 + j]);
+                }
+              }
+            }
           }
           epi_bar_sync();                                  // staging reuse; all pieces consumed
           if (et == 0)
@@ -493,6 +572,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(trace, 7);
   if (warp == 2) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
@@ -581,6 +661,25 @@ size_t plan_workspace(const Plan& pl) {
   return COUNTER_BYTES + (size_t)pl.grid * pl.bn * TILE_A * sizeof(float);
 }
 
+static unsigned g_trace_seq = 0;
+// debug timeline buffer (mapped pinned host memory): 64 launches x 1024 CTAs x 8 stamps, only when LIA_GEMM_TRACE is set
+unsigned long long* trace_buffer() {
+  static unsigned long long* buf = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* env = getenv("LIA_GEMM_TRACE");
+    if (env && atoi(env) != 0) {
+      void* p = nullptr;
+      if (cudaHostAlloc(&p, 64 * 1024 * 8 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
+        memset(p, 0, 64 * 1024 * 8 * sizeof(unsigned long long));
+        buf = reinterpret_cast<unsigned long long*>(p);
+      }
+    }
+  }
+  return buf;
+}
+
 template <bool SWAP, int BN, int STAGES>
 int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* flags,
            cudaStream_t stream) {
@@ -592,12 +691,29 @@ int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<pl.grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.streamk, pl.tiles_a, pl.tiles_b, ws, flags);
+  kern<<<pl.grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.streamk, pl.tiles_a, pl.tiles_b, ws, flags,
+                                                          trace_buffer() ? trace_buffer() + (size_t)(g_trace_seq++ % 64) * 1024 * 8 : nullptr);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
 }
 
 }  // namespace
+
+__global__ void debug_marker_kernel(unsigned long long* dst) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *dst = t;
+}
+// debug only: a 1-thread kernel that writes %globaltimer into slot `idx` of the marker area (last 1024 entries)
+extern "C" int lia_debug_marker(int idx, void* stream) {
+  unsigned long long* buf = trace_buffer();
+  if (!buf) return -1;
+  debug_marker_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(buf + 63 * 1024 * 8 + idx);
+  return 0;
+}
+
+// debug only (not part of include/lia_b200.h): host pointer to the last launch's timeline
+extern "C" const unsigned long long* lia_debug_gemm_trace(void) { return trace_buffer(); }
 
 extern "C" size_t lia_gemm_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
