@@ -239,8 +239,13 @@ def main():
         flops = sum(2.0 * M_ * N_ * K_ for M_, N_, K_, _ in big)
         ms = sum(t for *_, t in big)
         ach = flops / (ms / 1e3) / 1e12
+        traffic = None
+        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tj) and not args.layers and world == 1:
+            # DRAM read+write bytes per launch of this kernel from the committed `ncu --set full` capture
+            traffic = json.load(open(tj)).get("lia_gemm_tcgen05_kernel<0, 256, 4>", {}).get("dram_bytes_per_launch_avg")
         roof = {"kernel": "lia_gemm_tcgen05_kernel (prefill projections)", "bound": "tensor", "achieved": ach,
-                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": None,
+                "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic,
                 "launches": len(big), "avg_launch_ms": ms / len(big), "flops_per_launch": flops / len(big),
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step); burst "
                 + f"{pk['bf16_burst']}", "share_of_step": (ms / 1e3) / (sec / args.steps)}

@@ -23,6 +23,8 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const bf16* __rest
                                                               const bf16* __restrict__ vc, bf16* __restrict__ out,
                                                               float* __restrict__ ws, int T, int H, int cache_batch,
                                                               int b0, int t_chunk, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int LPR = D / 8;        // lanes per cached row (each lane owns 8 dims = 16 bytes)
   constexpr int RPW = 32 / LPR;     // rows per warp iteration
   constexpr int UNROLL = 4;
@@ -145,6 +147,8 @@ __global__ void __launch_bounds__(THREADS) attn_decode_kernel(const bf16* __rest
 
 template <int D>
 __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, bf16* __restrict__ out, int splits) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int bh = blockIdx.x;
   const int e = threadIdx.x;
   const float* src = ws + (size_t)bh * splits * (D + 2);
@@ -200,13 +204,13 @@ extern "C" int lia_attn_decode_bf16(const void* q, const void* k_cache, const vo
   bf16* op = reinterpret_cast<bf16*>(out);
   float* wsp = reinterpret_cast<float*>(workspace);
   if (d == 128) {
-    attn_decode_kernel<128><<<grid, THREADS, smem, stream>>>(qp, kp, vp, op, wsp, T, H, cache_batch, b0, t_chunk, splits);
+    lia_launch(attn_decode_kernel<128>, dim3(grid), dim3(THREADS), smem, stream, qp, kp, vp, op, wsp, T, H, cache_batch, b0, t_chunk, splits);
     LIA_LAUNCH_CHECK();
-    if (splits > 1) attn_decode_combine_kernel<128><<<B * H, 128, 0, stream>>>(wsp, op, splits);
+    if (splits > 1) lia_launch(attn_decode_combine_kernel<128>, dim3(B * H), dim3(128), 0, stream, wsp, op, splits);
   } else {
-    attn_decode_kernel<64><<<grid, THREADS, smem, stream>>>(qp, kp, vp, op, wsp, T, H, cache_batch, b0, t_chunk, splits);
+    lia_launch(attn_decode_kernel<64>, dim3(grid), dim3(THREADS), smem, stream, qp, kp, vp, op, wsp, T, H, cache_batch, b0, t_chunk, splits);
     LIA_LAUNCH_CHECK();
-    if (splits > 1) attn_decode_combine_kernel<64><<<B * H, 64, 0, stream>>>(wsp, op, splits);
+    if (splits > 1) lia_launch(attn_decode_combine_kernel<64>, dim3(B * H), dim3(64), 0, stream, wsp, op, splits);
   }
   LIA_LAUNCH_CHECK();
   return LIA_OK;

@@ -43,6 +43,8 @@ template <int D>
 __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
                                                                const bf16* __restrict__ vc, bf16* __restrict__ out,
                                                                int H, int S, int cache_batch, int b0) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int PITCH = D + 8;               // elements; (D+8)*2 bytes keeps ldmatrix rows on distinct banks
   constexpr int TILE_ELEMS = TILE * PITCH;
   constexpr int KSTEPS = D / 16;
@@ -231,7 +233,7 @@ int launch_prefill(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int
     configured = true;
   }
   const dim3 grid((S + TILE - 1) / TILE, H, B);
-  kern<<<grid, THREADS, SMEM, stream>>>(q, kc, vc, out, H, S, cache_batch, b0);
+  lia_launch(kern, dim3(grid), dim3(THREADS), SMEM, stream, q, kc, vc, out, H, S, cache_batch, b0);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
 }

@@ -1,5 +1,6 @@
 // Error plumbing, device info and small elementwise entry points of libliab200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -20,6 +21,15 @@ int lia_sm_count() {
       sms = 148;   // B200
   }
   return sms;
+}
+
+bool lia_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LIA_PDL");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 extern "C" int lia_abi_version(void) { return LIA_ABI_VERSION; }

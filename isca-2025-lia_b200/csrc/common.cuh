@@ -37,6 +37,30 @@ void lia_set_error(const char* fmt, ...);   // c_abi.cu
   } while (0)
 
 int lia_sm_count();   // cached, c_abi.cu
+bool lia_pdl_enabled();   // LIA_PDL=0 disables programmatic dependent launch, c_abi.cu
+
+#ifdef __CUDACC__
+#include <utility>
+// Every kernel is launched with programmatic stream serialization allowed (PDL): the next kernel's
+// CTAs may become resident and run their prologue (and, in the GEMM, prefetch weight tiles) while
+// the previous kernel drains; each kernel calls pdl_wait() before it touches anything a
+// predecessor produced.  Works unchanged inside CUDA-graph capture.
+template <typename... KArgs, typename... Args>
+inline cudaError_t lia_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = lia_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#endif
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
@@ -88,6 +112,10 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+
+// programmatic dependent launch (no-ops when the kernel was launched without the attribute)
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

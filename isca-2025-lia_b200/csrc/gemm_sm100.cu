@@ -323,6 +323,9 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) stamp(trace, 1);
+  // PDL: from here on the next kernel in the stream may become resident; this kernel touches nothing a
+  // predecessor produced until pdl_wait() (only weight tiles are fetched before it, see the producer)
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -330,16 +333,35 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       bool first_issue = true;
+      int npre = 0;
+      if (SWAP) {
+        // operand A is the weight matrix, which no kernel writes: fill the pipeline with weight tiles
+        // BEFORE waiting for the previous kernel (whose output is operand B)
+        Sched<SWAP> pre(k_blocks, tiles_a, tiles_b, streamk);
+        Work w;
+        while (npre < STAGES && pre.next(w)) {
+          for (int kb = w.kb0; kb < w.kb1 && npre < STAGES; ++kb, ++npre) {
+            mbar_expect_tx(full_bar(npre), L::STAGE_BYTES);
+            tma_load_2d(smem_base + npre * L::STAGE_BYTES, &tmA, kb * BLOCK_K, w.ta * TILE_A, full_bar(npre));
+          }
+        }
+      }
+      pdl_wait();
       Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
       Work w;
+      int idx = 0;
       while (sched.next(w)) {
-        for (int kb = w.kb0; kb < w.kb1; ++kb) {
-          mbar_wait(empty_bar(stage), phase ^ 1u);
+        for (int kb = w.kb0; kb < w.kb1; ++kb, ++idx) {
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
-          tma_load_2d(sa, &tmA, kb * BLOCK_K, w.ta * TILE_A, full_bar(stage));
-          tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));
+          if (idx < npre) {
+            tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));   // A tile already in flight
+          } else {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), L::STAGE_BYTES);
+            tma_load_2d(sa, &tmA, kb * BLOCK_K, w.ta * TILE_A, full_bar(stage));
+            tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));
+          }
           if (first_issue) {
             stamp(trace, 2);
             first_issue = false;
@@ -397,6 +419,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     // ===================== epilogue =====================
     const int ew = warp - EPI_WARP0;          // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
     const int et = threadIdx.x - EPI_WARP0 * 32;
+    pdl_wait();                               // residual / outputs / stream-K workspace belong to the stream order
     int acc = 0;
     uint32_t acc_phase = 0;
     Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
@@ -691,9 +714,9 @@ int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  kern<<<pl.grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, ep, pl.k_blocks, pl.streamk, pl.tiles_a, pl.tiles_b, ws, flags,
-                                                          trace_buffer() ? trace_buffer() + (size_t)(g_trace_seq++ % 64) * 1024 * 8 : nullptr);
-  LIA_LAUNCH_CHECK();
+  unsigned long long* tr = trace_buffer() ? trace_buffer() + (size_t)(g_trace_seq++ % 64) * 1024 * 8 : nullptr;
+  LIA_CUDA(lia_launch(kern, dim3(pl.grid), dim3(NUM_THREADS), L::TOTAL, stream, tmA, tmB, ep, pl.k_blocks, pl.streamk,
+                      pl.tiles_a, pl.tiles_b, ws, flags, tr));
   return LIA_OK;
 }
 

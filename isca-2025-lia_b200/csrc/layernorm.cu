@@ -14,6 +14,8 @@ template <int TPR, int VMAX>
 __global__ void __launch_bounds__(128) layernorm_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
                                                         const bf16* __restrict__ b, bf16* __restrict__ y, int rows,
                                                         int h, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int ROWS_PER_CTA = 128 / TPR;
   __shared__ float red[2][4];
   const int row = blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
@@ -94,9 +96,9 @@ extern "C" int lia_layernorm_bf16(const void* x, const void* w, const void* b, v
   const bf16* bp = reinterpret_cast<const bf16*>(b);
   bf16* yp = reinterpret_cast<bf16*>(y);
   if (h <= 2048) {
-    layernorm_kernel<32, 8><<<(rows + 3) / 4, 128, 0, stream>>>(xp, wp, bp, yp, rows, h, eps);
+    lia_launch(layernorm_kernel<32, 8>, dim3((rows + 3) / 4), dim3(128), 0, stream, xp, wp, bp, yp, rows, h, eps);
   } else {
-    layernorm_kernel<128, 16><<<rows, 128, 0, stream>>>(xp, wp, bp, yp, rows, h, eps);
+    lia_launch(layernorm_kernel<128, 16>, dim3(rows), dim3(128), 0, stream, xp, wp, bp, yp, rows, h, eps);
   }
   LIA_LAUNCH_CHECK();
   return LIA_OK;

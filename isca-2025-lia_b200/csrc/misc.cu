@@ -9,6 +9,8 @@ namespace {
 __global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ tok,
                                                     const bf16* __restrict__ pos, bf16* __restrict__ out, int S, int h,
                                                     int past_len, int vocab, int max_pos_rows) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;          // b*S + s
   const int s = row % S;
   long long id = ids[row];
@@ -32,6 +34,8 @@ __global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ 
 // (lia/generation_utils.py:872-880 + greedy_search.py:395)
 __global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ logits, int64_t* __restrict__ next, int V,
                                                      int suppress) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float sv[8];
   __shared__ int si[8];
   const bf16* row = logits + (size_t)blockIdx.x * V;
@@ -86,6 +90,8 @@ __global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ lo
 // projection (decoder.py:247, :317)
 __global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restrict__ x, const bf16* __restrict__ res,
                                                            bf16* __restrict__ out, size_t nvec) {
+  pdl_launch_dependents();
+  pdl_wait();
   for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < nvec; i += (size_t)gridDim.x * 256) {
     float a[8], c[8];
     unpack8(ldg_stream(x + i * 8), a);
@@ -103,6 +109,8 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
                                                         const bf16* __restrict__ v, bf16* __restrict__ q_out,
                                                         bf16* __restrict__ kc, bf16* __restrict__ vc, int S, int hq,
                                                         int pos0, int cache_batch, int b0, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;          // b*S + s
   const int b = row / S;
   const int s = row - b * S;
@@ -128,7 +136,7 @@ extern "C" int lia_kv_append_bf16(const void* q, const void* k, const void* v, v
   LIA_CHECK_ARG(q && k && v && q_out && k_cache && v_cache, "lia_kv_append_bf16: null pointer");
   LIA_CHECK_ARG(B > 0 && S > 0 && hq > 0 && hq % 8 == 0, "lia_kv_append_bf16: bad shape");
   LIA_CHECK_ARG(pos0 >= 0 && b0 >= 0 && b0 + B <= cache_batch, "lia_kv_append_bf16: batch window outside the cache");
-  kv_append_kernel<<<B * S, 128, 0, stream>>>(reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k),
+  lia_launch(kv_append_kernel, dim3(B * S), dim3(128), 0, stream, reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k),
                                               reinterpret_cast<const bf16*>(v), reinterpret_cast<bf16*>(q_out),
                                               reinterpret_cast<bf16*>(k_cache), reinterpret_cast<bf16*>(v_cache), S, hq, pos0,
                                               cache_batch, b0, q_scale);
@@ -142,7 +150,7 @@ extern "C" int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, cons
   LIA_CHECK_ARG(ids && embed_tokens && embed_positions && out, "lia_embed_bf16: null pointer");
   LIA_CHECK_ARG(B > 0 && S > 0 && h > 0 && h % 8 == 0, "lia_embed_bf16: bad shape B=%d S=%d h=%d", B, S, h);
   LIA_CHECK_ARG(past_len >= 0 && past_len + S + 2 <= max_pos_rows, "lia_embed_bf16: positions %d..%d exceed the table (%d rows)", past_len + 2, past_len + S + 1, max_pos_rows);
-  embed_kernel<<<B * S, 128, 0, stream>>>(ids, reinterpret_cast<const bf16*>(embed_tokens),
+  lia_launch(embed_kernel, dim3(B * S), dim3(128), 0, stream, ids, reinterpret_cast<const bf16*>(embed_tokens),
                                            reinterpret_cast<const bf16*>(embed_positions), reinterpret_cast<bf16*>(out), S, h,
                                            past_len, vocab, max_pos_rows);
   LIA_LAUNCH_CHECK();
@@ -153,7 +161,7 @@ extern "C" int lia_argmax_bf16(const void* logits, int64_t* next, int B, int V, 
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LIA_CHECK_ARG(logits && next && B > 0 && V > 0, "lia_argmax_bf16: bad arguments");
   LIA_CHECK_ARG(((size_t)V * 2) % 16 == 0 || B == 1, "lia_argmax_bf16: V*2 must be a multiple of 16 bytes for B > 1 (V=%d)", V);
-  argmax_kernel<<<B, 256, 0, stream>>>(reinterpret_cast<const bf16*>(logits), next, V, suppress_id);
+  lia_launch(argmax_kernel, dim3(B), dim3(256), 0, stream, reinterpret_cast<const bf16*>(logits), next, V, suppress_id);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
 }
@@ -167,7 +175,7 @@ extern "C" int lia_residual_add_bf16(const void* x, const void* residual, void* 
   size_t blocks = (nvec + 255) / 256;
   const size_t cap = (size_t)lia_sm_count() * 8;
   if (blocks > cap) blocks = cap;
-  residual_add_kernel<<<(unsigned)blocks, 256, 0, stream>>>(reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(residual),
+  lia_launch(residual_add_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, reinterpret_cast<const bf16*>(x), reinterpret_cast<const bf16*>(residual),
                                                             reinterpret_cast<bf16*>(out), nvec);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
