@@ -5,8 +5,9 @@
  * Boundary rules:
  *   - plain pointers and sizes only; every device pointer is owned by the caller
  *     (PyTorch on the Python side) -- the library never allocates or frees device
- *     memory;  the only allocations it owns are pinned host arenas and streamer
- *     handles created through the functions below.
+ *     memory behind the caller's back;  the only allocations it owns are the ones made
+ *     explicitly through the functions below: pinned host arenas, streamer handles and
+ *     the peer-mappable device arenas of the tensor-parallel path (lia_p2p_*).
  *   - all work is enqueued on the stream that is passed in; no hidden
  *     synchronisation (contrast lia/modeling_opt.py:1339 torch.cuda.synchronize()).
  *   - no C++ exceptions cross the ABI.  Functions return 0 on success, a negative
@@ -31,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LIA_ABI_VERSION 1
+#define LIA_ABI_VERSION 2
 
 typedef void* lia_stream_t; /* cudaStream_t */
 
@@ -129,6 +130,51 @@ int lia_argmax_bf16(const void* logits, int64_t* next, int B, int V, int suppres
  * projection under tensor parallelism (D:247, D:317; the reduce itself replaces D:60-68).
  * n = number of elements, n % 8 == 0. */
 int lia_residual_add_bf16(const void* x, const void* residual, void* out, size_t n, lia_stream_t stream);
+
+/* ---- tensor parallelism: row-parallel projection FUSED with its all-reduce and residual add.
+ *
+ * Replaces, for world > 1, the reference's  GPU GEMM -> .to('cpu') -> deepspeed_comm.all_reduce
+ * (oneCCL) -> .to('cuda') -> residual add  chain (gpu_linear_allreduce_compute D:60-77, then
+ * D:247 / D:317) with ONE kernel that exchanges partial tiles over NVLink peer memory while the
+ * remaining tiles are still being computed:
+ *     out = bf16( residual + bf16( sum_r  bf16( bf16(acc_r) + bias_r ) ) )
+ * (bias_r is this rank's share of the bias, i.e. bias / world, tensor_parallel.py:134; the sum over
+ * ranks is taken in fp32 in rank order, so every rank produces bit-identical results).
+ *   M <= 128 (decode): one-shot -- the CTA that finishes an output tile pushes it into every
+ *     peer's receive area, then reduces the `world` partials that landed in its own.
+ *   M >  128 (prefill): two-shot -- tile u is owned by rank u % world; the other ranks push their
+ *     partial to the owner, which reduces, adds the residual and writes the final tile into every
+ *     rank's `out` (which therefore must live inside the arena, at the same offset on every rank).
+ * All cross-GPU traffic goes through one symmetric "arena" per rank (lia_p2p_alloc), mapped into
+ * every peer with CUDA IPC.  Every rank must issue the same sequence of calls with the same shapes.
+ * Launches are safe under CUDA-graph replay (epochs live in device memory).  A peer that does
+ * not show up within LIA_TP_TIMEOUT_NS makes the kernel give up and set the arena's error word
+ * (lia_tp_error) instead of hanging the GPU. */
+#define LIA_TP_MAX_WORLD 8
+#define LIA_TP_MAX_UNITS 16384   /* output tiles per call */
+typedef struct LiaTpArgs {
+  int32_t rank, world;
+  void* arena[LIA_TP_MAX_WORLD]; /* arena[r] = rank r's arena mapped in this process; arena[rank] is local */
+  uint64_t ctl_off;              /* lia_tp_ctl_bytes() bytes, zero-initialised once (epoch, flags)      */
+  uint64_t recv_off;             /* receive area: 2 * recv_bytes (two parities)                          */
+  uint64_t recv_bytes;           /* >= lia_tp_recv_bytes(M, N, K, world)                                 */
+  uint64_t out_off;              /* M > 128 only: offset of `out` inside the arena                       */
+} LiaTpArgs;
+size_t lia_tp_ctl_bytes(void);
+size_t lia_tp_recv_bytes(int M, int N, int K, int world);
+int lia_gemm_allreduce_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
+                            int N, int K, const LiaTpArgs* tp, void* workspace, size_t workspace_bytes,
+                            lia_stream_t stream);
+/* reads (and clears) the arena's error word: 0 = ok, 1 = a peer timed out.  Synchronises the device. */
+int lia_tp_error(const LiaTpArgs* tp);
+
+/* peer-mappable device memory (cudaMalloc + CUDA IPC).  lia_p2p_alloc zero-fills the buffer and
+ * writes a 64-byte handle that another PROCESS passes to lia_p2p_open to map it. */
+#define LIA_P2P_HANDLE_BYTES 64
+int lia_p2p_alloc(size_t bytes, void** dev_ptr, void* handle_out);
+int lia_p2p_open(const void* handle, void** peer_ptr);
+int lia_p2p_close(void* peer_ptr);
+int lia_p2p_free(void* dev_ptr);
 
 /* ---- pinned host arena: replaces lia/cxl/numa_alloc.c (numa_alloc_node / numa_free_node) and
  * pin_memory (M:167-227).  Returns NULL on failure (message in lia_last_error()). */

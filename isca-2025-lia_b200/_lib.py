@@ -12,13 +12,21 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libliab200.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV = 0, 1, 2, 3
-ABI_VERSION = 1
+ABI_VERSION = 2
+TP_MAX_WORLD = 8
+P2P_HANDLE_BYTES = 64
 
 
 class LiaQkvArgs(ctypes.Structure):
     _fields_ = [("q_out", c_void_p), ("k_cache", c_void_p), ("v_cache", c_void_p),
                 ("hq", c_int32), ("S", c_int32), ("pos0", c_int32), ("cache_batch", c_int32),
                 ("b0", c_int32), ("q_scale", c_float)]
+
+
+class LiaTpArgs(ctypes.Structure):
+    _fields_ = [("rank", c_int32), ("world", c_int32), ("arena", c_void_p * TP_MAX_WORLD),
+                ("ctl_off", ctypes.c_uint64), ("recv_off", ctypes.c_uint64), ("recv_bytes", ctypes.c_uint64),
+                ("out_off", ctypes.c_uint64)]
 
 
 class LiaError(RuntimeError):
@@ -44,6 +52,15 @@ _PROTOTYPES = {
                                c_void_p]),
     "lia_argmax_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lia_residual_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "lia_tp_ctl_bytes": (c_size_t, []),
+    "lia_tp_recv_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "lia_gemm_allreduce_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                        POINTER(LiaTpArgs), c_void_p, c_size_t, c_void_p]),
+    "lia_tp_error": (c_int, [POINTER(LiaTpArgs)]),
+    "lia_p2p_alloc": (c_int, [c_size_t, POINTER(c_void_p), c_void_p]),
+    "lia_p2p_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "lia_p2p_close": (c_int, [c_void_p]),
+    "lia_p2p_free": (c_int, [c_void_p]),
     "lia_host_arena_alloc": (c_void_p, [c_size_t]),
     "lia_host_arena_free": (c_int, [c_void_p, c_size_t]),
     "lia_streamer_create": (c_void_p, [POINTER(c_void_p), c_int, c_size_t]),

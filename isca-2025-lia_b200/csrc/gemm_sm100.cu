@@ -43,7 +43,30 @@ constexpr int GROUP_M = 16;   // raster group (A tiles per group) for L2 reuse i
 constexpr int COUNTER_BYTES = 16384;
 constexpr int SWAP_LD = TILE_A + 4;   // fp32 staging pitch (floats) in SWAP mode
 
+constexpr int EPI_TP = 4;   // internal: row-parallel projection fused with its all-reduce + residual add
+constexpr int TP_CTL_INTS = 64;                       // [0] epoch  [1] CTA exit counter  [2] error word
+constexpr unsigned long long TP_TIMEOUT_NS = 4000000000ull;
+
+struct TpDev {
+  int rank, world;
+  char* arena[LIA_TP_MAX_WORLD];
+  unsigned long long ctl_off, recv_off, recv_bytes, out_off;
+  __device__ __forceinline__ int* ctl(int r) const { return reinterpret_cast<int*>(arena[r] + ctl_off); }
+  // data_flag[unit][src]: rank `src`'s partial of `unit` has landed in rank r's receive area
+  __device__ __forceinline__ int* data_flag(int r, int unit, int src) const {
+    return ctl(r) + TP_CTL_INTS + unit * LIA_TP_MAX_WORLD + src;
+  }
+  // done_flag[unit]: the owner's final tile of `unit` has landed in rank r's `out`
+  __device__ __forceinline__ int* done_flag(int r, int unit) const {
+    return ctl(r) + TP_CTL_INTS + LIA_TP_MAX_UNITS * LIA_TP_MAX_WORLD + unit;
+  }
+  __device__ __forceinline__ bf16* recv(int r, int parity) const {
+    return reinterpret_cast<bf16*>(arena[r] + recv_off + (unsigned long long)parity * recv_bytes);
+  }
+};
+
 struct EpiParams {
+  TpDev tp;
   const bf16* bias;
   const bf16* residual;
   bf16* out;
@@ -178,7 +201,7 @@ __device__ __forceinline__ void epilogue_load_bias8(const EpiParams& p, int n, f
   if (p.bias != nullptr) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias + n)), b);
 }
 __device__ __forceinline__ uint4 epilogue_load_residual8(const EpiParams& p, int m, int n) {
-  if (p.mode == LIA_EPI_BIAS_RESIDUAL) return ldg_stream(p.residual + (size_t)m * p.N + n);
+  if (p.mode == LIA_EPI_BIAS_RESIDUAL || p.mode == EPI_TP) return ldg_stream(p.residual + (size_t)m * p.N + n);
   return make_uint4(0, 0, 0, 0);
 }
 __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n, float* v) {
@@ -265,6 +288,33 @@ __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
 }
 __device__ __forceinline__ void st_release_gpu(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// wait until *flag reaches `epoch` (flags only grow; wrap-safe compare).  A peer that never shows up
+// must not hang the GPU: after TP_TIMEOUT_NS the error word is set and every later wait falls through.
+__device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
+  unsigned long long t0 = 0;
+  unsigned it = 0;
+  while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
+    if ((++it & 255u) == 0) {
+      if (*reinterpret_cast<volatile int*>(err) != 0) return;
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > TP_TIMEOUT_NS) {
+        atomicExch(err, 1);
+        return;
+      }
+    }
+  }
 }
 
 // optional per-CTA timeline (LIA_GEMM_TRACE=1): 8 globaltimer stamps per CTA in mapped host memory
@@ -422,6 +472,53 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     pdl_wait();                               // residual / outputs / stream-K workspace belong to the stream order
     int acc = 0;
     uint32_t acc_phase = 0;
+    // tensor-parallel fused all-reduce: this launch's epoch (same on every rank: all ranks issue the same
+    // call sequence) selects the receive-area parity and is the value flags are raised to
+    const bool tp_on = (p.mode == EPI_TP);
+    const TpDev& tp = p.tp;
+    int epoch = 0, parity = 0;
+    int* tp_err = nullptr;
+    if (tp_on) {
+      epoch = *reinterpret_cast<volatile int*>(tp.ctl(tp.rank)) + 1;
+      parity = epoch & 1;
+      tp_err = tp.ctl(tp.rank) + 2;
+    }
+    int pend_u = -1, pend_ta = 0, pend_tb = 0;   // NORMAL two-shot: one owned tile whose reduction is deferred
+    // NORMAL two-shot, owner side: all partials of tile u are here -> reduce in rank order, add the
+    // residual, write the final tile into EVERY rank's `out`, then raise done_flag[u] on the peers
+    auto tp_reduce_owned = [&](int u, int ta, int tb) {
+      if (et < tp.world && et != tp.rank) tp_spin(tp.data_flag(tp.rank, u, et), epoch, tp_err);
+      epi_bar_sync();
+      const bf16* rbase = tp.recv(tp.rank, parity) + (size_t)(u / tp.world) * tp.world * (TILE_A * BN);
+      constexpr int CPR = BN / 8;             // 16-byte chunks per tile row
+#pragma unroll 2
+      for (int c = et; c < TILE_A * CPR; c += 128) {
+        const int row = c / CPR, ch = c - row * CPR;
+        const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
+        if (m < p.M && n < p.N) {
+          float sum[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+          const uint4 res = ldg_stream(p.residual + (size_t)m * p.N + n);
+          for (int src = 0; src < tp.world; ++src) {
+            float f[8];
+            unpack8(__ldcg(reinterpret_cast<const uint4*>(rbase + ((size_t)src * TILE_A + row) * BN + ch * 8)), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum[i] += f[i];
+          }
+          float r[8];
+          unpack8(res, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum[i] = r[i] + bf16r(sum[i]);
+          const uint4 o = pack8(sum);
+          const size_t off = tp.out_off + ((size_t)m * p.N + n) * 2;
+          for (int r2 = 0; r2 < tp.world; ++r2) *reinterpret_cast<uint4*>(tp.arena[r2] + off) = o;
+        }
+      }
+      __threadfence_system();
+      epi_bar_sync();
+      if (et < tp.world && et != tp.rank) st_release_sys(tp.done_flag(et, u), epoch);
+    };
     Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
     Work w;
     while (sched.next(w)) {
@@ -488,10 +585,38 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             if (m < p.M && n < p.N) {
               float f[8];
               unpack8(q, f);
-              epilogue_store8(p, m, n, f);
+              if (tp_on) {
+                // partial tile (r2 = bf16(bf16(acc) + bias/world)) -> the owner's receive area, slot [tile][this rank]
+                if (p.bias != nullptr) {
+                  float b[8];
+                  epilogue_load_bias8(p, n, b);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i] + b[i]);
+                }
+                const int u = w.ta * tiles_b + w.tb;
+                bf16* dst = tp.recv(u % tp.world, parity) + ((size_t)(u / tp.world) * tp.world + tp.rank) * (TILE_A * BN) +
+                            (size_t)(ew * 32 + r) * BN + c0 + ch * 8;
+                *reinterpret_cast<uint4*>(dst) = pack8(f);
+              } else {
+                epilogue_store8(p, m, n, f);
+              }
             }
           }
           __syncwarp();
+        }
+        if (tp_on) {
+          const int u = w.ta * tiles_b + w.tb;
+          const int owner = u % tp.world;
+          __threadfence_system();
+          epi_bar_sync();
+          if (owner != tp.rank) {
+            if (et == 0) st_release_sys(tp.data_flag(owner, u, tp.rank), epoch);
+          } else {
+            // defer the reduction by one owned tile (= `world` tiles of MMA work) so the peers' partials are
+            // normally already here and the epilogue warps never stall the tensor pipe on NVLink latency
+            if (pend_u >= 0) tp_reduce_owned(pend_u, pend_ta, pend_tb);
+            pend_u = u; pend_ta = w.ta; pend_tb = w.tb;
+          }
         }
       } else {
         // tile rows = output features (TMEM lanes), columns = tokens: transpose through smem / workspace
@@ -578,7 +703,53 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (m < rows) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[j][i] = bf16r(f[j][i]);
-                  epilogue_finish8(p, m, n_col, f[j], biasf, resv[it0 + j]);
+                  if (!tp_on) {
+                    epilogue_finish8(p, m, n_col, f[j], biasf, resv[it0 + j]);
+                  } else {
+                    // one-shot all-reduce, push side: this rank's partial (r2 = bf16(bf16(acc) + bias/world)) goes
+                    // into slot [this rank] of EVERY rank's receive area (peers over NVLink, fire-and-forget)
+                    if (p.bias != nullptr) {
+#pragma unroll
+                      for (int i = 0; i < 8; ++i) f[j][i] = bf16r(f[j][i] + biasf[i]);
+                    }
+                    const uint4 o = pack8(f[j]);
+                    const size_t idx = ((size_t)tp.rank * BN + m) * p.N + n_col;
+                    for (int r2 = 0; r2 < tp.world; ++r2) *reinterpret_cast<uint4*>(tp.recv(r2, parity) + idx) = o;
+                  }
+                }
+              }
+            }
+          }
+          if (tp_on) {
+            // raise data_flag[tile][this rank] on every peer, wait for theirs, then reduce the `world` partials
+            // of this tile in rank order (fp32, one rounding) and add the residual -- identical on every rank
+            __threadfence_system();
+            epi_bar_sync();
+            if (et < tp.world && et != tp.rank) {
+              st_release_sys(tp.data_flag(et, w.ta, tp.rank), epoch);
+              tp_spin(tp.data_flag(tp.rank, w.ta, et), epoch, tp_err);
+            }
+            epi_bar_sync();
+            if (n_ok) {
+              const bf16* rbase = tp.recv(tp.rank, parity);
+#pragma unroll
+              for (int it = 0; it < ITERS; ++it) {
+                const int m = m0 + it * 8;
+                if (m < rows) {
+                  float sum[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+                  for (int src = 0; src < tp.world; ++src) {
+                    float g[8];
+                    unpack8(__ldcg(reinterpret_cast<const uint4*>(rbase + ((size_t)src * BN + m) * p.N + n_col)), g);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sum[i] += g[i];
+                  }
+                  float r[8];
+                  unpack8(resv[it], r);
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) sum[i] = r[i] + bf16r(sum[i]);
+                  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = pack8(sum);
                 }
               }
             }
@@ -590,6 +761,31 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+    }
+    if (tp_on) {
+      if (!SWAP) {
+        if (pend_u >= 0) tp_reduce_owned(pend_u, pend_ta, pend_tb);
+        // this CTA's tiles that other ranks own: wait until their final values have landed in our `out`
+        // (the kernel must not complete before its output is complete); 128 threads poll in parallel
+        Sched<SWAP> s2(k_blocks, tiles_a, tiles_b, streamk);
+        Work w2;
+        int i = 0;
+        while (s2.next(w2)) {
+          const int u = w2.ta * tiles_b + w2.tb;
+          if (u % tp.world != tp.rank && (i++ & 127) == et) tp_spin(tp.done_flag(tp.rank, u), epoch, tp_err);
+        }
+        epi_bar_sync();
+      }
+      // the last CTA to leave publishes the epoch for the next launch (every CTA read it on entry)
+      if (et == 0) {
+        __threadfence();
+        int* ctl = tp.ctl(tp.rank);
+        if (atomicAdd(ctl + 1, 1) == (int)gridDim.x - 1) {
+          ctl[1] = 0;
+          __threadfence();
+          *reinterpret_cast<volatile int*>(ctl) = epoch;
+        }
+      }
     }
   }
 
@@ -649,9 +845,21 @@ struct Plan {
   int tiles_a, tiles_b, k_blocks;
 };
 
+// CTAs available to one GEMM launch: the SM count, or LIA_GEMM_MAX_CTAS when set (lets two launches that
+// talk to each other share one GPU: tests/test_gpu_tp.py runs a 2-rank exchange on a single device)
+int gemm_cta_budget() {
+  int sms = lia_sm_count();
+  const char* env = getenv("LIA_GEMM_MAX_CTAS");
+  if (env) {
+    const int v = atoi(env);
+    if (v > 0 && v < sms) sms = v;
+  }
+  return sms;
+}
+
 Plan make_plan(int M, int N, int K) {
   Plan pl;
-  const int sms = lia_sm_count();
+  const int sms = gemm_cta_budget();
   pl.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   pl.swap = (M <= 128);
   pl.streamk = 0;
@@ -743,15 +951,14 @@ extern "C" size_t lia_gemm_workspace_bytes(int M, int N, int K) {
   return plan_workspace(make_plan(M, N, K));
 }
 
-extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
-                             int N, int K, int epilogue, const LiaQkvArgs* qkv, void* workspace, size_t workspace_bytes,
-                             lia_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  LIA_CHECK_ARG(M > 0 && N > 0 && K > 0, "lia_gemm_bf16: M,N,K must be positive (got %d,%d,%d)", M, N, K);
-  LIA_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "lia_gemm_bf16: K and N must be multiples of 8 (got K=%d N=%d)", K, N);
-  LIA_CHECK_ARG(A && W, "lia_gemm_bf16: null operand");
-  LIA_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "lia_gemm_bf16: operands must be 16-byte aligned");
-  LIA_CHECK_ARG(epilogue >= LIA_EPI_BIAS && epilogue <= LIA_EPI_QKV, "lia_gemm_bf16: unknown epilogue %d", epilogue);
+static int gemm_impl(const void* A, const void* W, const void* bias, const void* residual, void* out, int M, int N, int K,
+                     int epilogue, const LiaQkvArgs* qkv, const LiaTpArgs* tp, void* workspace, size_t workspace_bytes,
+                     cudaStream_t stream) {
+  const char* fn = tp ? "lia_gemm_allreduce_bf16" : "lia_gemm_bf16";
+  LIA_CHECK_ARG(M > 0 && N > 0 && K > 0, "%s: M,N,K must be positive (got %d,%d,%d)", fn, M, N, K);
+  LIA_CHECK_ARG(K % 8 == 0 && N % 8 == 0, "%s: K and N must be multiples of 8 (got K=%d N=%d)", fn, K, N);
+  LIA_CHECK_ARG(A && W, "%s: null operand", fn);
+  LIA_CHECK_ARG(((uintptr_t)A % 16 == 0) && ((uintptr_t)W % 16 == 0), "%s: operands must be 16-byte aligned", fn);
   EpiParams ep{};
   ep.bias = reinterpret_cast<const bf16*>(bias);
   ep.residual = reinterpret_cast<const bf16*>(residual);
@@ -771,10 +978,29 @@ extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, con
     ep.hq = qkv->hq; ep.S = qkv->S; ep.pos0 = qkv->pos0; ep.cache_batch = qkv->cache_batch; ep.b0 = qkv->b0;
     ep.q_scale = qkv->q_scale;
   } else {
-    LIA_CHECK_ARG(out != nullptr, "lia_gemm_bf16: null output");
-    if (epilogue == LIA_EPI_BIAS_RESIDUAL) LIA_CHECK_ARG(residual != nullptr, "lia_gemm_bf16: residual epilogue needs residual");
+    LIA_CHECK_ARG(out != nullptr, "%s: null output", fn);
+    if (epilogue == LIA_EPI_BIAS_RESIDUAL || epilogue == EPI_TP)
+      LIA_CHECK_ARG(residual != nullptr, "%s: residual epilogue needs residual", fn);
   }
   Plan pl = make_plan(M, N, K);
+  if (tp != nullptr) {
+    LIA_CHECK_ARG(tp->world >= 2 && tp->world <= LIA_TP_MAX_WORLD && tp->rank >= 0 && tp->rank < tp->world,
+                  "%s: bad rank/world %d/%d", fn, tp->rank, tp->world);
+    for (int r = 0; r < tp->world; ++r) LIA_CHECK_ARG(tp->arena[r] != nullptr, "%s: arena[%d] is not mapped", fn, r);
+    LIA_CHECK_ARG(tp->ctl_off % 16 == 0 && tp->recv_off % 16 == 0 && tp->recv_bytes % 16 == 0, "%s: arena offsets must be 16-byte aligned", fn);
+    LIA_CHECK_ARG(tp->recv_bytes >= lia_tp_recv_bytes(M, N, K, tp->world), "%s: receive area of %llu bytes is too small (need %zu)", fn,
+                  (unsigned long long)tp->recv_bytes, lia_tp_recv_bytes(M, N, K, tp->world));
+    const int units = pl.swap ? pl.tiles_a : pl.tiles_a * pl.tiles_b;
+    LIA_CHECK_ARG(units <= LIA_TP_MAX_UNITS, "%s: %d output tiles exceed LIA_TP_MAX_UNITS", fn, units);
+    if (!pl.swap) {
+      const char* base = reinterpret_cast<const char*>(tp->arena[tp->rank]);
+      LIA_CHECK_ARG(reinterpret_cast<const char*>(out) == base + tp->out_off, "%s: for M > 128 `out` must live in the arena at out_off", fn);
+    }
+    ep.tp.rank = tp->rank;
+    ep.tp.world = tp->world;
+    for (int r = 0; r < tp->world; ++r) ep.tp.arena[r] = reinterpret_cast<char*>(tp->arena[r]);
+    ep.tp.ctl_off = tp->ctl_off; ep.tp.recv_off = tp->recv_off; ep.tp.recv_bytes = tp->recv_bytes; ep.tp.out_off = tp->out_off;
+  }
   float* ws = nullptr;
   int* flags = nullptr;
   if (pl.swap && pl.streamk) {
@@ -803,4 +1029,47 @@ extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, con
     if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, flags, stream);
   }
+}
+
+extern "C" int lia_gemm_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
+                             int N, int K, int epilogue, const LiaQkvArgs* qkv, void* workspace, size_t workspace_bytes,
+                             lia_stream_t stream_) {
+  LIA_CHECK_ARG(epilogue >= LIA_EPI_BIAS && epilogue <= LIA_EPI_QKV, "lia_gemm_bf16: unknown epilogue %d", epilogue);
+  return gemm_impl(A, W, bias, residual, out, M, N, K, epilogue, qkv, nullptr, workspace, workspace_bytes,
+                   reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// ------------------------------------------------------------------ tensor-parallel fused projection + all-reduce
+extern "C" size_t lia_tp_ctl_bytes(void) {
+  return (size_t)(TP_CTL_INTS + LIA_TP_MAX_UNITS * LIA_TP_MAX_WORLD + LIA_TP_MAX_UNITS) * sizeof(int);
+}
+
+extern "C" size_t lia_tp_recv_bytes(int M, int N, int K, int world) {
+  if (M <= 0 || N <= 0 || K <= 0 || world <= 0) return 0;
+  const Plan pl = make_plan(M, N, K);
+  if (pl.swap) return (size_t)world * pl.bn * N * sizeof(bf16);                       // [src][bn rows][N]
+  const size_t units = (size_t)pl.tiles_a * pl.tiles_b;
+  return ((units + world - 1) / world) * world * (size_t)(TILE_A * pl.bn) * sizeof(bf16);   // [owned tile][src][128][bn]
+}
+
+extern "C" int lia_gemm_allreduce_bf16(const void* A, const void* W, const void* bias, const void* residual, void* out,
+                                       int M, int N, int K, const LiaTpArgs* tp, void* workspace, size_t workspace_bytes,
+                                       lia_stream_t stream_) {
+  LIA_CHECK_ARG(tp != nullptr, "lia_gemm_allreduce_bf16: null LiaTpArgs");
+  return gemm_impl(A, W, bias, residual, out, M, N, K, EPI_TP, nullptr, tp, workspace, workspace_bytes,
+                   reinterpret_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int lia_tp_error(const LiaTpArgs* tp) {
+  LIA_CHECK_ARG(tp != nullptr && tp->rank >= 0 && tp->rank < LIA_TP_MAX_WORLD && tp->arena[tp->rank] != nullptr, "lia_tp_error: bad LiaTpArgs");
+  LIA_CUDA(cudaDeviceSynchronize());
+  int* err = reinterpret_cast<int*>(reinterpret_cast<char*>(tp->arena[tp->rank]) + tp->ctl_off) + 2;
+  int v = 0;
+  LIA_CUDA(cudaMemcpy(&v, err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (v != 0) {
+    LIA_CUDA(cudaMemset(err, 0, sizeof(int)));
+    lia_set_error("tensor-parallel exchange timed out waiting for a peer (error word %d)", v);
+    return 1;
+  }
+  return 0;
 }

@@ -6,6 +6,8 @@
 //                     layer) and the per-forward stream/buffer churn (:1195-1212, :1288-1316) with ONE
 //                     cudaMemcpyAsync per layer slab on a private copy stream, double-buffered against
 //                     the compute stream with events -- no device-wide synchronisation.
+#include <string.h>
+
 #include <vector>
 
 #include "common.cuh"
@@ -130,5 +132,53 @@ extern "C" int lia_streamer_destroy(LiaStreamer* s) {
   for (auto e : s->released) cudaEventDestroy(e);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   delete s;
+  return LIA_OK;
+}
+
+// ---------------------------------------------------------------- peer-mappable device arenas (tensor parallelism)
+// One cudaMalloc'd arena per rank, exported with CUDA IPC and mapped by every peer process: the fused
+// projection + all-reduce kernel (gemm_sm100.cu) stores partial tiles and flags straight into peers'
+// arenas over NVLink.  Replaces the reference's oneCCL/MPI/POSIX-shm messenger (csrc/cpu/comm/messager.h:13-62,
+// shm_reduction.h) -- there the partial sums travel GPU -> host -> shm/CCL -> host -> GPU (decoder.py:60-68).
+static_assert(sizeof(cudaIpcMemHandle_t) == LIA_P2P_HANDLE_BYTES, "LIA_P2P_HANDLE_BYTES must match cudaIpcMemHandle_t");
+
+extern "C" int lia_p2p_alloc(size_t bytes, void** dev_ptr, void* handle_out) {
+  LIA_CHECK_ARG(bytes > 0 && dev_ptr != nullptr && handle_out != nullptr, "lia_p2p_alloc: bad arguments");
+  void* p = nullptr;
+  LIA_CUDA(cudaMalloc(&p, bytes));
+  cudaError_t e = cudaMemset(p, 0, bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    lia_set_error("lia_p2p_alloc(%zu): %s", bytes, cudaGetErrorString(e));
+    cudaFree(p);
+    (void)cudaGetLastError();
+    return LIA_ERR_CUDA;
+  }
+  memcpy(handle_out, &h, sizeof(h));
+  *dev_ptr = p;
+  return LIA_OK;
+}
+
+extern "C" int lia_p2p_open(const void* handle, void** peer_ptr) {
+  LIA_CHECK_ARG(handle != nullptr && peer_ptr != nullptr, "lia_p2p_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, sizeof(h));
+  void* p = nullptr;
+  LIA_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  *peer_ptr = p;
+  return LIA_OK;
+}
+
+extern "C" int lia_p2p_close(void* peer_ptr) {
+  if (peer_ptr == nullptr) return LIA_OK;
+  LIA_CUDA(cudaIpcCloseMemHandle(peer_ptr));
+  return LIA_OK;
+}
+
+extern "C" int lia_p2p_free(void* dev_ptr) {
+  if (dev_ptr == nullptr) return LIA_OK;
+  LIA_CUDA(cudaFree(dev_ptr));
   return LIA_OK;
 }

@@ -101,12 +101,14 @@ def _check_policy(p, what):
 class _Workspace:
     """Activation scratch for up to ``rows`` token rows -- allocated once per shape."""
 
-    def __init__(self, cfg, layout, rows, batch, device):
+    def __init__(self, cfg, layout, rows, batch, device, arena=None):
         h, hq, fq = cfg.hidden_size, layout.hq, layout.fq
         e = lambda *s: torch.empty(*s, dtype=BF16, device=device)  # noqa: E731
         self.rows = rows
-        self.ln, self.q, self.ctx, self.x1, self.ffn = e(rows, h), e(rows, hq), e(rows, hq), e(rows, h), e(rows, fq)
-        self.tp = e(rows, h) if layout.tp > 1 else None
+        self.arena = arena          # tp.PeerArena: row-parallel projections run fused with their all-reduce
+        self.ln, self.q, self.ctx, self.ffn = e(rows, h), e(rows, hq), e(rows, hq), e(rows, fq)
+        self.x1 = arena.tensor("x1", (rows, h)) if arena is not None else e(rows, h)
+        self.tp = e(rows, h) if layout.tp > 1 and arena is None else None
         shapes = []
         for m in {rows, batch}:
             shapes += [(m, 3 * hq, h), (m, h, hq), (m, fq, h), (m, h, fq), (m, cfg.vocab_size, h)]
@@ -128,12 +130,25 @@ class _GenState:
         self.beam_idx = torch.zeros(self.Tmax, B, dtype=torch.long, device=dev)
         self.prompt = torch.zeros(B, S, dtype=torch.int64, device=dev)
         self.steps_tok = torch.zeros(max(new, 1), B, dtype=torch.int64, device=dev)
-        self.x = torch.empty(B * S, cfg.hidden_size, dtype=BF16, device=dev)
-        self.xd = torch.empty(B, cfg.hidden_size, dtype=BF16, device=dev)
+        mb = max(1, B // max(1, num_minibatch))
+        rows = max(mb * S, B)
+        h = cfg.hidden_size
+        self.arena = None
+        if model.tp_world > 1 and tp_mod.fused_enabled() and dev.type == "cuda":
+            # the residual stream lives in a peer-mapped arena: owners of a prefill tile write the reduced
+            # result straight into every rank's copy (include/lia_b200.h, lia_gemm_allreduce_bf16)
+            lay, lib = model.layout, _lib.load()
+            recv = max(lib.lia_tp_recv_bytes(m, h, k, model.tp_world) for m in {mb * S, B} for k in (lay.hq, lay.fq))
+            self.arena = tp_mod.PeerArena(model.tp_rank, model.tp_world, dev, recv,
+                                          [("x", B * S * h * 2), ("xd", B * h * 2), ("x1", rows * h * 2)])
+            self.x = self.arena.tensor("x", (B * S, h))
+            self.xd = self.arena.tensor("xd", (B, h))
+        else:
+            self.x = torch.empty(B * S, h, dtype=BF16, device=dev)
+            self.xd = torch.empty(B, h, dtype=BF16, device=dev)
         self.xn = torch.empty(B, cfg.hidden_size, dtype=BF16, device=dev)
         self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
-        mb = max(1, B // max(1, num_minibatch))
-        self.ws = _Workspace(cfg, model.layout, max(mb * S, B), B, dev)
+        self.ws = _Workspace(cfg, model.layout, rows, B, dev, self.arena)
         self.graphs = {}
         self.calls = 0
 
@@ -284,8 +299,12 @@ class OPTDecoder:
             ops.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
         else:
             ops.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
+        arena = ws.arena
+        big = M > 128                       # prefill tiles are finished by their owner rank, which writes `out` remotely
         if self.tp_world == 1:
             ops.gemm(ctx, v["o_w"], v["o_b"], out=x1, epilogue=EPI_BIAS_RESIDUAL, residual=rows, workspace=ws.gemm)  # decoder.py:228-229
+        elif arena is not None:             # decoder.py:60-68 + 247 as one kernel over NVLink peer memory
+            ops.gemm_allreduce(ctx, v["o_w"], v["o_b"], rows, x1, arena.args(x1 if big else None), workspace=ws.gemm)
         else:
             part = ws.tp[:M]
             ops.gemm(ctx, v["o_w"], v["o_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)        # decoder.py:60-68
@@ -295,6 +314,8 @@ class OPTDecoder:
         ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)      # decoder.py:285
         if self.tp_world == 1:
             ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=rows, epilogue=EPI_BIAS_RESIDUAL, residual=x1, workspace=ws.gemm)  # decoder.py:309-310
+        elif arena is not None:             # decoder.py:316-317
+            ops.gemm_allreduce(ffn, v["fc2_w"], v["fc2_b"], x1, rows, arena.args(rows if big else None), workspace=ws.gemm)
         else:
             part = ws.tp[:M]
             ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)
@@ -434,7 +455,10 @@ class OPTForCausalLM:
     def _state(self, B, S, new, num_minibatch):
         key = (B, S, new, num_minibatch)
         if key not in self._states:
-            self._states.clear()                      # one live shape at a time: caches are large
+            for old in self._states.values():          # one live shape at a time: caches are large
+                if old.arena is not None:
+                    old.arena.close()
+            self._states.clear()
             self._states[key] = _GenState(self, B, S, new, num_minibatch)
         return self._states[key]
 
@@ -506,6 +530,8 @@ class OPTForCausalLM:
         out_dev = torch.cat([st.prompt, st.steps_tok[:new].t()], dim=1)
         out = out_dev.to(input_ids.device)                                               # D2H of the result (syncs)
         torch.cuda.synchronize(self.device)
+        if st.arena is not None:
+            st.arena.check()                          # a peer that never showed up: raise instead of returning garbage
         lat = [ev[i].elapsed_time(ev[i + 1]) / 1e3 for i in range(new)]
         self.last_timing = {"prefill_s": lat[0], "decode_s": lat[1:], "total_s": sum(lat)}
         if self.config.token_latency:

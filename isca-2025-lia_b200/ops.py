@@ -81,6 +81,27 @@ def gemm(a, w, bias, out=None, epilogue=EPI_BIAS, residual=None, qkv=None, works
     return out
 
 
+def gemm_allreduce(a, w, bias, residual, out, tp_args, workspace=None):
+    """Row-parallel projection fused with its all-reduce and residual add (world > 1):
+    out = residual + sum_over_ranks(a_r @ w_r.T + bias_r)  (decoder.py:60-77 + 247/317).
+    ``tp_args`` is a LiaTpArgs from tp.PeerArena.args(); for M > 128 ``out`` must be an arena tensor."""
+    _req(a, "a"); _req(w, "w"); _req(residual, "residual"); _req(out, "out")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.LiaError(f"gemm_allreduce: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if bias is not None:
+        _req(bias, "bias")
+    ws_ptr, ws_bytes = (None, 0)
+    if workspace is not None:
+        ws_ptr, ws_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
+    check(_lib.load().lia_gemm_allreduce_bf16(_p(a), _p(w), _p(bias), _p(residual), _p(out), M, N, K,
+                                              ctypes.byref(tp_args), ws_ptr, ws_bytes, _stream()),
+          "lia_gemm_allreduce_bf16")
+    count_launches()
+    return out
+
+
 def qkv_args(q_out, k_cache, v_cache, S, pos0, b0, scale):
     """k_cache/v_cache: [Tmax, Bc, H, d] time-major (attentions.py:471-472)."""
     _req(q_out, "q_out"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")

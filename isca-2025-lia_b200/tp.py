@@ -1,14 +1,23 @@
 """Tensor-parallel plumbing: one process per GPU, torch.distributed (NCCL over NVLink 5 /
-NVSwitch) for bootstrap and the all-reduce that follows each row-parallel projection.
+NVSwitch) for bootstrap.
 
 Replaces the reference's GPU GEMM -> .to('cpu') -> deepspeed_comm.all_reduce (oneCCL) ->
-.to('cuda') bounce (decoder.py:60-77) with an in-place device all-reduce on the compute
-stream.  Sharding rule: weights.shard_layer (tensor_parallel.py:30-141).
+.to('cuda') bounce (decoder.py:60-77).  Two data paths:
+  * fused (default on GPUs): ``PeerArena`` -- one peer-mapped device arena per rank (CUDA IPC over
+    NVLink); the row-parallel projection, its all-reduce and the residual add are ONE kernel
+    (``ops.gemm_allreduce`` -> lia_gemm_allreduce_bf16) that exchanges partial tiles through the
+    arenas while the remaining tiles are still being computed.
+  * plain (``LIA_TP_FUSED=0``, and the CPU/gloo tests): GEMM -> in-place ``all_reduce`` on the
+    compute stream -> residual add.
+Sharding rule: weights.shard_layer (tensor_parallel.py:30-141).
 """
+import ctypes
 import os
 
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 _group = None
 
@@ -57,3 +66,119 @@ def max_over_ranks(value, device):
     t = torch.tensor([value], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=_group)
     return float(t.item())
+
+
+def fused_enabled():
+    """Fused projection + all-reduce over peer memory (default) vs GEMM -> NCCL all-reduce -> add."""
+    return os.environ.get("LIA_TP_FUSED", "1") != "0"
+
+
+class _RawCuda:
+    """__cuda_array_interface__ carrier: lets torch view arena bytes without owning them."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+
+
+def _align(n, a=256):
+    return (int(n) + a - 1) // a * a
+
+
+class PeerArena:
+    """One symmetric device arena per rank, mapped into every peer (lia_p2p_*; CUDA IPC).
+
+    Layout (identical on every rank): ``ctl`` (epoch/flags) | receive area (2 parities) | named
+    activation buffers the prefill path needs to be remotely writable.  ``handles`` are exchanged
+    with ``all_gather_object`` on the (NCCL or gloo) process group -- plumbing only; the data path
+    is the kernel's own loads/stores over NVLink."""
+
+    def __init__(self, rank, world, device, recv_bytes, buffers, group=None, exchange=None):
+        lib = _lib.load()
+        self.rank, self.world, self.device = rank, world, torch.device(device)
+        self.ctl_off = 0
+        self.recv_off = _align(lib.lia_tp_ctl_bytes())
+        self.recv_bytes = _align(recv_bytes)
+        off = self.recv_off + 2 * self.recv_bytes
+        self.offsets = {}
+        for name, nbytes in buffers:
+            self.offsets[name] = (off, int(nbytes))
+            off = _align(off + nbytes)
+        self.nbytes = off
+        ptr = ctypes.c_void_p()
+        handle = (ctypes.c_uint8 * _lib.P2P_HANDLE_BYTES)()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.lia_p2p_alloc(self.nbytes, ctypes.byref(ptr), handle), "lia_p2p_alloc")
+        self.local = ptr.value
+        self.peers = [None] * world
+        self.peers[rank] = self.local
+        mine = bytes(handle)
+        if exchange is None:
+            gathered = [None] * world
+            dist.all_gather_object(gathered, mine, group=group)
+        else:
+            gathered = exchange(mine)            # tests: single-process stand-in
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                continue
+            if isinstance(gathered[r], int):     # same-process stand-in: already a device pointer
+                self.peers[r] = gathered[r]
+                continue
+            h = (ctypes.c_uint8 * _lib.P2P_HANDLE_BYTES).from_buffer_copy(gathered[r])
+            pp = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                _lib.check(lib.lia_p2p_open(h, ctypes.byref(pp)), "lia_p2p_open")
+            self.peers[r] = pp.value
+            self._opened.append(pp.value)
+        self._bytes = torch.as_tensor(_RawCuda(self.local, self.nbytes), device=self.device)
+
+    def tensor(self, name, shape, dtype=torch.bfloat16):
+        off, nbytes = self.offsets[name]
+        t = self._bytes[off:off + nbytes].view(dtype)
+        n = 1
+        for s_ in shape:
+            n *= s_
+        return t[:n].view(*shape)
+
+    def offset_of(self, t):
+        off = t.data_ptr() - self.local
+        if not (0 <= off < self.nbytes):
+            raise _lib.LiaError("tensor does not live in the peer arena")
+        return off
+
+    def args(self, out=None):
+        """LiaTpArgs for one call; ``out`` (an arena tensor) is needed for M > 128."""
+        a = _lib.LiaTpArgs()
+        a.rank, a.world = self.rank, self.world
+        for r in range(self.world):
+            a.arena[r] = self.peers[r]
+        a.ctl_off, a.recv_off, a.recv_bytes = self.ctl_off, self.recv_off, self.recv_bytes
+        a.out_off = self.offset_of(out) if out is not None else 0
+        return a
+
+    def check(self):
+        """Raise if a kernel gave up waiting for a peer (synchronises the device)."""
+        rc = _lib.load().lia_tp_error(ctypes.byref(self.args()))
+        if rc != 0:
+            raise _lib.LiaError(_lib.last_error())
+
+    def close(self, sync=True):
+        """Unmap the peers and free the local arena.  ``sync``: barrier first so that no peer still
+        uses this rank's memory (skipped in __del__, where a collective could hang at exit)."""
+        lib = _lib.load()
+        if getattr(self, "local", None):
+            torch.cuda.synchronize(self.device)
+            if sync and dist.is_initialized() and self._opened:
+                dist.barrier()
+            self._bytes = None
+            for p in self._opened:
+                lib.lia_p2p_close(p)
+            self._opened = []
+            lib.lia_p2p_free(self.local)
+            self.local = None
+
+    def __del__(self):
+        try:
+            self.close(sync=False)
+        except Exception:
+            pass

@@ -37,10 +37,19 @@ def test_header_symbols_exported_and_bound(built):
 
 def test_abi_version_and_struct_layout(built):
     lib = built.load()
-    assert lib.lia_abi_version() == built.ABI_VERSION == 1
+    assert lib.lia_abi_version() == built.ABI_VERSION == 2
     # LiaQkvArgs: 3 pointers + 5 int32 + 1 float, natural alignment
     assert ctypes.sizeof(built.LiaQkvArgs) == 48
     assert built.LiaQkvArgs.hq.offset == 24 and built.LiaQkvArgs.q_scale.offset == 44
+    # LiaTpArgs: 2 int32 + 8 pointers + 4 uint64
+    assert ctypes.sizeof(built.LiaTpArgs) == 8 + 64 + 32 and built.LiaTpArgs.ctl_off.offset == 72
+    assert lib.lia_tp_ctl_bytes() == (64 + 16384 * 8 + 16384) * 4
+    # receive area: one-shot [world][bn][N] bf16 for M <= 128, two-shot [owned tiles][world][128][bn] above
+    assert lib.lia_tp_recv_bytes(64, 7168, 896, 8) == 8 * 64 * 7168 * 2
+    assert lib.lia_tp_recv_bytes(8192, 7168, 896, 8) == (64 * 28 // 8) * 8 * 128 * 256 * 2
+    tpargs = built.LiaTpArgs()
+    rc = lib.lia_gemm_allreduce_bf16(16, 16, None, 16, 16, 8, 16, 16, ctypes.byref(tpargs), None, 0, None)
+    assert rc == -1 and "rank/world" in built.last_error()
 
 
 def test_argument_errors_are_reported_not_crashed(built):

@@ -1,0 +1,115 @@
+"""Tensor-parallel data path on real hardware.
+
+* ``test_fused_allreduce_two_ranks_one_gpu``: the fused projection + all-reduce + residual kernel
+  (lia_gemm_allreduce_bf16) with ``world`` simulated ranks sharing ONE GPU -- each rank's launch is
+  capped to a slice of the SMs (LIA_GEMM_MAX_CTAS) and runs on its own stream, so the launches are
+  co-resident and really exchange tiles/flags through their arenas.  Checks the one-shot (M <= 128)
+  and two-shot (M > 128) protocols, epoch/parity reuse over repeated calls and CUDA-graph replay,
+  bit-identical results on every rank, and the reference's rounding points (D:60-77, D:247).
+* ``test_tp_multi_gpu``: needs >= 2 GPUs (skipped on a 1-GPU box): torchrun tests/tp_worker.py.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ref(As, Ws, bs, res):
+    """bf16(residual + bf16(sum_r bf16(bf16(A_r W_r^T) + b_r))), fp32 sums in rank order."""
+    tot = None
+    for a, w, b in zip(As, Ws, bs):
+        part = (a.float() @ w.float().t()).to(BF16)
+        part = (part.float() + b.float()).to(BF16).float()
+        tot = part if tot is None else tot + part
+    return (res.float() + tot.to(BF16).float()).to(BF16)
+
+
+@pytest.mark.parametrize("world,M,N,K", [(2, 8, 256, 512), (2, 64, 1024, 1536), (4, 64, 512, 256),
+                                         (2, 384, 512, 256), (2, 1000, 768, 320), (4, 512, 1024, 128)])
+def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, monkeypatch):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import lia_b200  # noqa: F401
+    from lia_b200 import _lib, ops, tp
+    lib = _lib.load()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    monkeypatch.setenv("LIA_GEMM_MAX_CTAS", str(sms // world))
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device="cuda").manual_seed(world * 1000 + M)
+    rnd = lambda *s: (torch.randn(*s, generator=g, device=dev) * 0.5).to(BF16)  # noqa: E731
+    As = [rnd(M, K) for _ in range(world)]
+    Ws = [rnd(N, K) for _ in range(world)]
+    bs = [rnd(N) for _ in range(world)]
+    res = rnd(M, N)
+    recv = lib.lia_tp_recv_bytes(M, N, K, world)
+    arenas = [tp.PeerArena(r, world, dev, recv, [("out", M * N * 2)], exchange=lambda mine: [0] * world)
+              for r in range(world)]
+    for a in arenas:
+        for r in range(world):
+            a.peers[r] = arenas[r].local
+    outs = [a.tensor("out", (M, N)) for a in arenas]
+    wss = [ops.GemmWorkspace(ops.GemmWorkspace.bytes_for([(M, N, K)]), dev) for _ in range(world)]
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    want = _ref(As, Ws, bs, res)
+
+    def launch_all():
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                ops.gemm_allreduce(As[r], Ws[r], bs[r], res, outs[r], arenas[r].args(outs[r] if M > 128 else None),
+                                   workspace=wss[r])
+
+    torch.cuda.synchronize()
+    for rep in range(3):                       # epochs 1..3: both receive parities, flag reuse
+        for o in outs:
+            o.zero_()
+        torch.cuda.synchronize()
+        launch_all()
+        torch.cuda.synchronize()
+        for a in arenas:
+            a.check()
+        for r in range(1, world):
+            assert torch.equal(outs[0], outs[r]), f"rank {r} differs from rank 0 (rep {rep})"
+        err = (outs[0].float() - want.float()).abs().max().item()
+        scale = want.float().abs().max().item()
+        assert err <= 2 ** -7 * scale, (rep, err, scale)      # a couple of bf16 ulps (K-loop summation order only)
+    first = outs[0].clone()
+    # CUDA-graph replay: kernel arguments are frozen, epochs advance in device memory
+    graphs = []
+    for r in range(world):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=streams[r]):
+            ops.gemm_allreduce(As[r], Ws[r], bs[r], res, outs[r], arenas[r].args(outs[r] if M > 128 else None),
+                               workspace=wss[r])
+        graphs.append(gr)
+    for rep in range(2):
+        for o in outs:
+            o.zero_()
+        torch.cuda.synchronize()
+        for r in range(world):
+            with torch.cuda.stream(streams[r]):
+                graphs[r].replay()
+        torch.cuda.synchronize()
+        for a in arenas:
+            a.check()
+        for r in range(world):
+            assert torch.equal(outs[r], first), f"graph replay {rep}: rank {r} differs"
+    for a in arenas:
+        a._opened = []
+        a.close(sync=False)
+
+
+@pytest.mark.parametrize("nproc", [2])
+def test_tp_multi_gpu(nproc):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < nproc:
+        pytest.skip(f"needs {nproc} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + os.getpid() % 300), os.path.join(ROOT, "tests", "tp_worker.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-4000:]
+    assert "TP_WORKER_OK" in r.stdout, r.stdout[-4000:]
