@@ -140,6 +140,16 @@ def cpu_baseline(args, cfg, steps=1, warmup=0):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner) go to stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    try:
+        return _main(args, real_stdout)
+    finally:
+        real_stdout.flush()
+
+
+def _main(args, json_out):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     import lia_b200
@@ -163,7 +173,7 @@ def main():
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": config, "cpu_baseline": cb,
                 "e2e": {"value": cb["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out)
         return 0
 
     import torch
@@ -269,7 +279,8 @@ def main():
                 "roofline": roof, "roofline_decode": roof_dec}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"], _ = cpu_baseline(args, cfg)
-        print(json.dumps(line))
+        print(json.dumps(line), file=json_out)
+        json_out.flush()
     tp.barrier()
     return 0
 

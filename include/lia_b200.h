@@ -141,10 +141,12 @@ int lia_residual_add_bf16(const void* x, const void* residual, void* out, size_t
  * (bias_r is this rank's share of the bias, i.e. bias / world, tensor_parallel.py:134; the sum over
  * ranks is taken in fp32 in rank order, so every rank produces bit-identical results).
  *   M <= 128 (decode): one-shot -- the CTA that finishes an output tile pushes it into every
- *     peer's receive area, then reduces the `world` partials that landed in its own.
+ *     peer's receive area as {4 data bytes, epoch} words (data and validity arrive together: one
+ *     one-way NVLink latency, no fence, no flag), then reduces the `world` partials in its own.
  *   M >  128 (prefill): two-shot -- tile u is owned by rank u % world; the other ranks push their
  *     partial to the owner, which reduces, adds the residual and writes the final tile into every
- *     rank's `out` (which therefore must live inside the arena, at the same offset on every rank).
+ *     rank's `out` (which therefore must live inside the arena, at the same offset on every rank);
+ *     flags trail their data by one tile so no warp ever waits out an NVLink round trip.
  * All cross-GPU traffic goes through one symmetric "arena" per rank (lia_p2p_alloc), mapped into
  * every peer with CUDA IPC.  Every rank must issue the same sequence of calls with the same shapes.
  * Launches are safe under CUDA-graph replay (epochs live in device memory).  A peer that does

@@ -49,6 +49,7 @@ constexpr unsigned long long TP_TIMEOUT_NS = 4000000000ull;
 
 struct TpDev {
   int rank, world;
+  int opts;   // tuning probes: bit0 = do not trigger dependents early (PDL), bit1 = back off between failed polls
   char* arena[LIA_TP_MAX_WORLD];
   unsigned long long ctl_off, recv_off, recv_bytes, out_off;
   __device__ __forceinline__ int* ctl(int r) const { return reinterpret_cast<int*>(arena[r] + ctl_off); }
@@ -175,7 +176,7 @@ __device__ __forceinline__ void epilogue_finish8(const EpiParams& p, int m, int 
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
     *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
-  } else if (p.mode == LIA_EPI_BIAS_RESIDUAL) {
+  } else if (p.mode == LIA_EPI_BIAS_RESIDUAL || p.mode == EPI_TP) {
     float r[8];
     unpack8(res, r);
 #pragma unroll
@@ -238,32 +239,34 @@ struct Work {
 
 template <bool SWAP>
 struct Sched {
+  // 32-bit arithmetic throughout: tiles_a * k_blocks * gridDim.x < 2^31 is checked on the host (64-bit
+  // divisions are software routines of ~100 instructions each and this code is inlined into three roles)
   int k_blocks, tiles_a, tiles_b;
-  long long pos, end;   // SWAP: flat k-block position; NORMAL: unit index / count
+  unsigned pos, end;   // SWAP: flat k-block position; NORMAL: unit index / count
   __device__ Sched(int k_blocks_, int tiles_a_, int tiles_b_, int streamk) : k_blocks(k_blocks_), tiles_a(tiles_a_), tiles_b(tiles_b_) {
     if (SWAP) {
       if (streamk) {
-        const long long total = (long long)tiles_a * k_blocks;
+        const unsigned total = (unsigned)tiles_a * (unsigned)k_blocks;
         pos = total * blockIdx.x / gridDim.x;
         end = total * (blockIdx.x + 1) / gridDim.x;
       } else {   // whole tiles only
-        pos = ((long long)tiles_a * blockIdx.x / gridDim.x) * k_blocks;
-        end = ((long long)tiles_a * (blockIdx.x + 1) / gridDim.x) * k_blocks;
+        pos = ((unsigned)tiles_a * blockIdx.x / gridDim.x) * (unsigned)k_blocks;
+        end = ((unsigned)tiles_a * (blockIdx.x + 1) / gridDim.x) * (unsigned)k_blocks;
       }
     } else {
       pos = blockIdx.x;
-      end = (long long)tiles_a * tiles_b;
+      end = (unsigned)tiles_a * (unsigned)tiles_b;
     }
   }
   __device__ bool next(Work& w) {
     if (pos >= end) return false;
     if (SWAP) {
-      w.ta = (int)(pos / k_blocks);
+      w.ta = (int)(pos / (unsigned)k_blocks);
       w.tb = 0;
-      w.kb0 = (int)(pos - (long long)w.ta * k_blocks);
-      const long long left = end - pos;
-      w.kb1 = (left < (long long)(k_blocks - w.kb0)) ? w.kb0 + (int)left : k_blocks;
-      pos += w.kb1 - w.kb0;
+      w.kb0 = (int)(pos - (unsigned)w.ta * (unsigned)k_blocks);
+      const unsigned left = end - pos;
+      w.kb1 = (left < (unsigned)(k_blocks - w.kb0)) ? w.kb0 + (int)left : k_blocks;
+      pos += (unsigned)(w.kb1 - w.kb0);
     } else {
       const int u = (int)pos;
       const int group_size = GROUP_M * tiles_b;
@@ -298,6 +301,14 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
 __device__ __forceinline__ void st_release_sys(int* p, int v) {
   asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_volatile_v4(uint4* p, const uint4& v) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
 // wait until *flag reaches `epoch` (flags only grow; wrap-safe compare).  A peer that never shows up
 // must not hang the GPU: after TP_TIMEOUT_NS the error word is set and every later wait falls through.
 __device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
@@ -317,17 +328,17 @@ __device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
   }
 }
 
-// optional per-CTA timeline (LIA_GEMM_TRACE=1): 8 globaltimer stamps per CTA in mapped host memory
+// optional per-CTA timeline (LIA_GEMM_TRACE=1): 16 globaltimer stamps per CTA (<= 512 CTAs) in mapped host memory
 __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
   if (trace != nullptr) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
-    trace[blockIdx.x * 8 + i] = t;
+    trace[blockIdx.x * 16 + i] = t;
   }
 }
 
 // ------------------------------------------------------------------ the kernel
-template <bool SWAP, int BN, int STAGES>
+template <bool SWAP, int BN, int STAGES, bool TP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
@@ -375,7 +386,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (threadIdx.x == 0) stamp(trace, 1);
   // PDL: from here on the next kernel in the stream may become resident; this kernel touches nothing a
   // predecessor produced until pdl_wait() (only weight tiles are fetched before it, see the producer)
-  pdl_launch_dependents();
+  if (!((SWAP ? p.mode == EPI_TP : TP) && (p.tp.opts & 1))) pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -474,56 +485,97 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t acc_phase = 0;
     // tensor-parallel fused all-reduce: this launch's epoch (same on every rank: all ranks issue the same
     // call sequence) selects the receive-area parity and is the value flags are raised to
-    const bool tp_on = (p.mode == EPI_TP);
+    // NORMAL (prefill): TP is a separate instantiation, the plain projections carry none of this code.
+    // SWAP (decode): ONE function serves plain and fused projections -- a decode step alternates between them
+    // every few microseconds, and two ~100 KB kernels evicting each other from the instruction cache cost
+    // ~10 us per switch (measured); a run-time branch keeps the whole step on one resident code image.
+    const bool tp_on = SWAP ? (p.mode == EPI_TP) : TP;
     const TpDev& tp = p.tp;
     int epoch = 0, parity = 0;
     int* tp_err = nullptr;
     if (tp_on) {
-      epoch = *reinterpret_cast<volatile int*>(tp.ctl(tp.rank)) + 1;
+      epoch = (tp.opts & 64) ? 1 : *reinterpret_cast<volatile int*>(tp.ctl(tp.rank)) + 1;
       parity = epoch & 1;
       tp_err = tp.ctl(tp.rank) + 2;
     }
     int pend_u = -1, pend_ta = 0, pend_tb = 0;   // NORMAL two-shot: one owned tile whose reduction is deferred
+    // NORMAL two-shot: flags are raised one tile late.  A flag may only be raised after a system-scope fence has
+    // seen the remote stores it covers acknowledged (~5 us over NVLink); a tile later the acknowledgements are
+    // long back, so the fence costs nothing and the epilogue warps never sit out an NVLink round trip.
+    int sig_data_u = -1, sig_done_u = -1;
+    auto tp_flush_signals = [&]() {
+      if (sig_data_u >= 0 || sig_done_u >= 0) {
+        __threadfence_system();
+        epi_bar_sync();
+        if (sig_data_u >= 0 && et == 0) st_release_sys(tp.data_flag(sig_data_u % tp.world, sig_data_u, tp.rank), epoch);
+        if (sig_done_u >= 0 && et < tp.world && et != tp.rank) st_release_sys(tp.done_flag(et, sig_done_u), epoch);
+        sig_data_u = sig_done_u = -1;
+      }
+    };
     // NORMAL two-shot, owner side: all partials of tile u are here -> reduce in rank order, add the
     // residual, write the final tile into EVERY rank's `out`, then raise done_flag[u] on the peers
     auto tp_reduce_owned = [&](int u, int ta, int tb) {
-      if (et < tp.world && et != tp.rank) tp_spin(tp.data_flag(tp.rank, u, et), epoch, tp_err);
+      if (et < tp.world && et != tp.rank && !(tp.opts & 4)) tp_spin(tp.data_flag(tp.rank, u, et), epoch, tp_err);
       epi_bar_sync();
       const bf16* rbase = tp.recv(tp.rank, parity) + (size_t)(u / tp.world) * tp.world * (TILE_A * BN);
       constexpr int CPR = BN / 8;             // 16-byte chunks per tile row
-#pragma unroll 2
-      for (int c = et; c < TILE_A * CPR; c += 128) {
-        const int row = c / CPR, ch = c - row * CPR;
-        const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
-        if (m < p.M && n < p.N) {
-          float sum[8];
+      constexpr int CH = 8;                   // chunks per thread in flight: (1 + world) x 8 independent 16-byte loads
+      static_assert(SWAP || (TILE_A * CPR) % (128 * CH) == 0, "tile must split into whole batches");
+#pragma unroll 1
+      for (int c0 = et; c0 < TILE_A * CPR; c0 += 128 * CH) {
+        float sum[CH][8];
+        uint4 res[CH];
+        bool ok[CH];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sum[i] = 0.f;
-          const uint4 res = ldg_stream(p.residual + (size_t)m * p.N + n);
-          for (int src = 0; src < tp.world; ++src) {
-            float f[8];
-            unpack8(__ldcg(reinterpret_cast<const uint4*>(rbase + ((size_t)src * TILE_A + row) * BN + ch * 8)), f);
+        for (int j = 0; j < CH; ++j) {
+          const int c = c0 + j * 128;
+          const int row = c / CPR, ch = c - row * CPR;
+          const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
+          ok[j] = (m < p.M && n < p.N);
+          res[j] = ok[j] ? ldg_stream(p.residual + (size_t)m * p.N + n) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) sum[i] += f[i];
+          for (int i = 0; i < 8; ++i) sum[j][i] = 0.f;
+        }
+        for (int src = 0; src < tp.world; ++src) {
+          uint4 v[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int c = c0 + j * 128;
+            const int row = c / CPR, ch = c - row * CPR;
+            v[j] = ok[j] ? __ldcg(reinterpret_cast<const uint4*>(rbase + ((size_t)src * TILE_A + row) * BN + ch * 8)) : make_uint4(0, 0, 0, 0);
           }
-          float r[8];
-          unpack8(res, r);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) sum[i] = r[i] + bf16r(sum[i]);
-          const uint4 o = pack8(sum);
-          const size_t off = tp.out_off + ((size_t)m * p.N + n) * 2;
-          for (int r2 = 0; r2 < tp.world; ++r2) *reinterpret_cast<uint4*>(tp.arena[r2] + off) = o;
+          for (int j = 0; j < CH; ++j) {
+            float f[8];
+            unpack8(v[j], f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum[j][i] += f[i];
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < CH; ++j) {
+          if (ok[j]) {
+            const int c = c0 + j * 128;
+            const int row = c / CPR, ch = c - row * CPR;
+            const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
+            float r[8];
+            unpack8(res[j], r);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) sum[j][i] = r[i] + bf16r(sum[j][i]);
+            const uint4 o = pack8(sum[j]);
+            const size_t off = tp.out_off + ((size_t)m * p.N + n) * 2;
+            for (int r2 = 0; r2 < tp.world; ++r2) *reinterpret_cast<uint4*>(tp.arena[r2] + off) = o;
+          }
         }
       }
-      __threadfence_system();
-      epi_bar_sync();
-      if (et < tp.world && et != tp.rank) st_release_sys(tp.done_flag(et, u), epoch);
+      sig_done_u = u;                         // done_flag[u] is raised by the next tp_flush_signals()
     };
     Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
     Work w;
     while (sched.next(w)) {
       // SWAP: this thread finishes columns [n_col, n_col+8) of rows m0, m0+8, ... -- fetch what the
       // epilogue needs besides the accumulator (bias, residual) BEFORE waiting for the MMAs
+      if (tp_on && !SWAP) tp_flush_signals();
       constexpr int ITERS = SWAP ? BN / 8 : 1;
       const int c8 = et & 15, m0 = et >> 4;
       const int rows = min(BN, p.M);
@@ -607,11 +659,10 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (tp_on) {
           const int u = w.ta * tiles_b + w.tb;
           const int owner = u % tp.world;
-          __threadfence_system();
-          epi_bar_sync();
           if (owner != tp.rank) {
-            if (et == 0) st_release_sys(tp.data_flag(owner, u, tp.rank), epoch);
+            sig_data_u = u;
           } else {
+            epi_bar_sync();                      // our own partial is complete in our receive area
             // defer the reduction by one owned tile (= `world` tiles of MMA work) so the peers' partials are
             // normally already here and the epilogue warps never stall the tensor pipe on NVLink latency
             if (pend_u >= 0) tp_reduce_owned(pend_u, pend_ta, pend_tb);
@@ -650,11 +701,11 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (et == 0) st_release_gpu(flags + blockIdx.x, 1);
         } else {
           // contributors are CTAs c+1, c+2, ... whose spans start inside this tile
-          const long long total = (long long)tiles_a * k_blocks;
-          const long long tile_end = (long long)(w.ta + 1) * k_blocks;
+          const unsigned total = (unsigned)tiles_a * (unsigned)k_blocks;
+          const unsigned tile_end = (unsigned)(w.ta + 1) * (unsigned)k_blocks;
           int last_c = blockIdx.x;
           if (!full) {
-            while (last_c + 1 < (int)gridDim.x && total * (last_c + 1) / gridDim.x < tile_end) ++last_c;
+            while (last_c + 1 < (int)gridDim.x && total * (unsigned)(last_c + 1) / gridDim.x < tile_end) ++last_c;
             if (et == 0) {
               for (int c = blockIdx.x + 1; c <= last_c; ++c)
                 while (ld_acquire_gpu(flags + c) == 0) {
@@ -667,8 +718,18 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           // the loads of a batch (own sums from smem, pieces from L2) are all in flight together
           if (n_ok) {
             constexpr int RB = ITERS < 4 ? ITERS : 4;
-#pragma unroll
+            // (a real loop, not unrolled: this code runs once per tile and its size is paid in instruction-cache
+            // misses -- the unrolled epilogue was ~120 KB of SASS)
+#pragma unroll 1
             for (int it0 = 0; it0 < ITERS; it0 += RB) {
+              uint4 rcur[RB];      // this batch's prefetched residual rows (register select, no dynamic indexing)
+#pragma unroll
+              for (int j = 0; j < RB; ++j) {
+                rcur[j] = resv[j];
+#pragma unroll
+                for (int b = 1; b < ITERS / RB; ++b)
+                  if (it0 == b * RB) rcur[j] = resv[b * RB + j];
+              }
               float f[RB][8];
 #pragma unroll
               for (int j = 0; j < RB; ++j) {
@@ -703,56 +764,116 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                 if (m < rows) {
 #pragma unroll
                   for (int i = 0; i < 8; ++i) f[j][i] = bf16r(f[j][i]);
-                  if (!tp_on) {
-                    epilogue_finish8(p, m, n_col, f[j], biasf, resv[it0 + j]);
+                  if (!tp_on || (tp.opts & 32)) {
+                    epilogue_finish8(p, m, n_col, f[j], biasf, rcur[j]);
                   } else {
                     // one-shot all-reduce, push side: this rank's partial (r2 = bf16(bf16(acc) + bias/world)) goes
-                    // into slot [this rank] of EVERY rank's receive area (peers over NVLink, fire-and-forget)
+                    // into slot [this rank] of EVERY rank's receive area (peers over NVLink, fire-and-forget).
+                    // "LL" framing: every 8-byte word is {4 bytes of data, epoch}, so data and its validity
+                    // arrive together -- no fence, no separate flag, ONE one-way NVLink latency per exchange.
                     if (p.bias != nullptr) {
 #pragma unroll
                       for (int i = 0; i < 8; ++i) f[j][i] = bf16r(f[j][i] + biasf[i]);
                     }
                     const uint4 o = pack8(f[j]);
-                    const size_t idx = ((size_t)tp.rank * BN + m) * p.N + n_col;
-                    for (int r2 = 0; r2 < tp.world; ++r2) *reinterpret_cast<uint4*>(tp.recv(r2, parity) + idx) = o;
+                    const uint4 lo = make_uint4(o.x, (uint32_t)epoch, o.y, (uint32_t)epoch);
+                    const uint4 hi = make_uint4(o.z, (uint32_t)epoch, o.w, (uint32_t)epoch);
+                    const size_t idx = (((size_t)tp.rank * BN + m) * p.N + n_col) >> 2;   // uint4 index: 2 per 8 values
+                    for (int r2 = 0; r2 < tp.world; ++r2) {
+                      if ((tp.opts & 8) && r2 != tp.rank) continue;   // timing probe only: no remote stores
+                      uint4* dst = reinterpret_cast<uint4*>(tp.recv(r2, parity)) + idx;
+                      st_volatile_v4(dst, lo);
+                      st_volatile_v4(dst + 1, hi);
+                    }
                   }
                 }
               }
             }
           }
           if (tp_on) {
-            // raise data_flag[tile][this rank] on every peer, wait for theirs, then reduce the `world` partials
-            // of this tile in rank order (fp32, one rounding) and add the residual -- identical on every rank
-            __threadfence_system();
-            epi_bar_sync();
-            if (et < tp.world && et != tp.rank) {
-              st_release_sys(tp.data_flag(et, w.ta, tp.rank), epoch);
-              tp_spin(tp.data_flag(tp.rank, w.ta, et), epoch, tp_err);
-            }
-            epi_bar_sync();
-            if (n_ok) {
-              const bf16* rbase = tp.recv(tp.rank, parity);
+            // reduce side: poll the `world` partials of this thread's values in OUR receive area until their
+            // epoch words match, sum them in rank order (fp32, one rounding), add the residual: every rank
+            // computes bit-identical results
+            if (et == 0) stamp(trace, 8);
+            if (n_ok && !(tp.opts & 32)) {
+              const uint4* rb = reinterpret_cast<const uint4*>(tp.recv(tp.rank, parity));
+              constexpr int RB2 = ITERS < 4 ? ITERS : 4;
+#pragma unroll 1
+              for (int it0 = 0; it0 < ITERS; it0 += RB2) {
+                uint4 rcur[RB2];
 #pragma unroll
-              for (int it = 0; it < ITERS; ++it) {
-                const int m = m0 + it * 8;
-                if (m < rows) {
-                  float sum[8];
+                for (int j = 0; j < RB2; ++j) {
+                  rcur[j] = resv[j];
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) sum[i] = 0.f;
-                  for (int src = 0; src < tp.world; ++src) {
+                  for (int b = 1; b < ITERS / RB2; ++b)
+                    if (it0 == b * RB2) rcur[j] = resv[b * RB2 + j];
+                }
+                float sum[RB2][8];
+#pragma unroll
+                for (int j = 0; j < RB2; ++j)
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) sum[j][i] = 0.f;
+                for (int src = 0; src < tp.world; ++src) {
+                  uint4 lo[RB2], hi[RB2];
+                  unsigned long long t0 = 0;
+                  unsigned spins = 0;
+                  bool ok;
+                  do {
+                    ok = true;
+#pragma unroll
+                    for (int j = 0; j < RB2; ++j) {
+                      const int m = m0 + (it0 + j) * 8;
+                      if (m < rows) {
+                        const uint4* q = rb + ((((size_t)src * BN + m) * p.N + n_col) >> 2);
+                        lo[j] = ld_volatile_v4(q);
+                        hi[j] = ld_volatile_v4(q + 1);
+                      }
+                    }
+#pragma unroll
+                    for (int j = 0; j < RB2; ++j) {
+                      const int m = m0 + (it0 + j) * 8;
+                      if (m < rows)
+                        ok = ok && lo[j].y == (uint32_t)epoch && lo[j].w == (uint32_t)epoch && hi[j].y == (uint32_t)epoch &&
+                             hi[j].w == (uint32_t)epoch;
+                    }
+                    if (tp.opts & 4) ok = true;               // timing probe only: do not wait for the peer (results are garbage)
+                    if (!ok && (tp.opts & 2)) __nanosleep(100);
+                    if (!ok && (++spins & 255u) == 0) {       // a peer that never shows up must not hang the GPU
+                      if (*reinterpret_cast<volatile int*>(tp_err) != 0) break;
+                      unsigned long long t;
+                      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+                      if (t0 == 0) t0 = t;
+                      else if (t - t0 > TP_TIMEOUT_NS) {
+                        atomicExch(tp_err, 1);
+                        break;
+                      }
+                    }
+                  } while (!ok);
+#pragma unroll
+                  for (int j = 0; j < RB2; ++j) {
                     float g[8];
-                    unpack8(__ldcg(reinterpret_cast<const uint4*>(rbase + ((size_t)src * BN + m) * p.N + n_col)), g);
+                    unpack_bf16x2(lo[j].x, g[0], g[1]);
+                    unpack_bf16x2(lo[j].z, g[2], g[3]);
+                    unpack_bf16x2(hi[j].x, g[4], g[5]);
+                    unpack_bf16x2(hi[j].z, g[6], g[7]);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) sum[i] += g[i];
+                    for (int i = 0; i < 8; ++i) sum[j][i] += g[i];
                   }
-                  float r[8];
-                  unpack8(resv[it], r);
+                }
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) sum[i] = r[i] + bf16r(sum[i]);
-                  *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = pack8(sum);
+                for (int j = 0; j < RB2; ++j) {
+                  const int m = m0 + (it0 + j) * 8;
+                  if (m < rows) {
+                    float r[8];
+                    unpack8(rcur[j], r);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) sum[j][i] = r[i] + bf16r(sum[j][i]);
+                    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = pack8(sum[j]);
+                  }
                 }
               }
             }
+            if (et == 0) stamp(trace, 11);
           }
           epi_bar_sync();                                  // staging reuse; all pieces consumed
           if (et == 0)
@@ -764,7 +885,9 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
     if (tp_on) {
       if (!SWAP) {
+        tp_flush_signals();
         if (pend_u >= 0) tp_reduce_owned(pend_u, pend_ta, pend_tb);
+        tp_flush_signals();
         // this CTA's tiles that other ranks own: wait until their final values have landed in our `out`
         // (the kernel must not complete before its output is complete); 128 threads poll in parallel
         Sched<SWAP> s2(k_blocks, tiles_a, tiles_b, streamk);
@@ -772,12 +895,12 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         int i = 0;
         while (s2.next(w2)) {
           const int u = w2.ta * tiles_b + w2.tb;
-          if (u % tp.world != tp.rank && (i++ & 127) == et) tp_spin(tp.done_flag(tp.rank, u), epoch, tp_err);
+          if (u % tp.world != tp.rank && (i++ & 127) == et && !(tp.opts & 4)) tp_spin(tp.done_flag(tp.rank, u), epoch, tp_err);
         }
         epi_bar_sync();
       }
       // the last CTA to leave publishes the epoch for the next launch (every CTA read it on entry)
-      if (et == 0) {
+      if (et == 0 && !(tp.opts & 16)) {
         __threadfence();
         int* ctl = tp.ctl(tp.rank);
         if (atomicAdd(ctl + 1, 1) == (int)gridDim.x - 1) {
@@ -894,6 +1017,10 @@ size_t plan_workspace(const Plan& pl) {
 
 static unsigned g_trace_seq = 0;
 // debug timeline buffer (mapped pinned host memory): 64 launches x 1024 CTAs x 8 stamps, only when LIA_GEMM_TRACE is set
+// The stamps live in DEVICE memory (stamping into mapped host memory made every traced kernel wait out
+// PCIe write acknowledgements at its end); lia_debug_gemm_trace() copies them to a host mirror.
+constexpr size_t TRACE_WORDS = (size_t)64 * 512 * 16;
+static unsigned long long* g_trace_host = nullptr;
 unsigned long long* trace_buffer() {
   static unsigned long long* buf = nullptr;
   static bool tried = false;
@@ -902,30 +1029,38 @@ unsigned long long* trace_buffer() {
     const char* env = getenv("LIA_GEMM_TRACE");
     if (env && atoi(env) != 0) {
       void* p = nullptr;
-      if (cudaHostAlloc(&p, 64 * 1024 * 8 * sizeof(unsigned long long), cudaHostAllocMapped) == cudaSuccess) {
-        memset(p, 0, 64 * 1024 * 8 * sizeof(unsigned long long));
+      if (cudaMalloc(&p, TRACE_WORDS * sizeof(unsigned long long)) == cudaSuccess) {
+        cudaMemset(p, 0, TRACE_WORDS * sizeof(unsigned long long));
         buf = reinterpret_cast<unsigned long long*>(p);
+        g_trace_host = reinterpret_cast<unsigned long long*>(calloc(TRACE_WORDS, sizeof(unsigned long long)));
       }
     }
   }
   return buf;
 }
 
-template <bool SWAP, int BN, int STAGES>
-int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* flags,
+template <bool SWAP, int BN, int STAGES, bool TP>
+int launch_tp(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* flags,
            cudaStream_t stream) {
   using L = SmemLayout<SWAP, BN, STAGES>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
-  auto kern = lia_gemm_tcgen05_kernel<SWAP, BN, STAGES>;
+  auto kern = lia_gemm_tcgen05_kernel<SWAP, BN, STAGES, TP>;
   static bool configured = false;
   if (!configured) {
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
-  unsigned long long* tr = trace_buffer() ? trace_buffer() + (size_t)(g_trace_seq++ % 64) * 1024 * 8 : nullptr;
+  unsigned long long* tr = trace_buffer() ? trace_buffer() + (size_t)(g_trace_seq++ % 64) * 512 * 16 : nullptr;
   LIA_CUDA(lia_launch(kern, dim3(pl.grid), dim3(NUM_THREADS), L::TOTAL, stream, tmA, tmB, ep, pl.k_blocks, pl.streamk,
                       pl.tiles_a, pl.tiles_b, ws, flags, tr));
   return LIA_OK;
+}
+
+template <bool SWAP, int BN, int STAGES>
+int launch(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, float* ws, int* flags,
+           cudaStream_t stream) {
+  if (!SWAP && ep.mode == EPI_TP) return launch_tp<SWAP, BN, STAGES, true>(pl, tmA, tmB, ep, ws, flags, stream);
+  return launch_tp<SWAP, BN, STAGES, false>(pl, tmA, tmB, ep, ws, flags, stream);
 }
 
 }  // namespace
@@ -939,12 +1074,17 @@ __global__ void debug_marker_kernel(unsigned long long* dst) {
 extern "C" int lia_debug_marker(int idx, void* stream) {
   unsigned long long* buf = trace_buffer();
   if (!buf) return -1;
-  debug_marker_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(buf + 63 * 1024 * 8 + idx);
+  debug_marker_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(buf + 63 * 512 * 16 + idx);
   return 0;
 }
 
 // debug only (not part of include/lia_b200.h): host pointer to the last launch's timeline
-extern "C" const unsigned long long* lia_debug_gemm_trace(void) { return trace_buffer(); }
+extern "C" const unsigned long long* lia_debug_gemm_trace(void) {
+  if (!trace_buffer() || !g_trace_host) return nullptr;
+  cudaDeviceSynchronize();
+  cudaMemcpy(g_trace_host, trace_buffer(), TRACE_WORDS * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  return g_trace_host;
+}
 
 extern "C" size_t lia_gemm_workspace_bytes(int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -983,6 +1123,8 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
       LIA_CHECK_ARG(residual != nullptr, "%s: residual epilogue needs residual", fn);
   }
   Plan pl = make_plan(M, N, K);
+  LIA_CHECK_ARG((long long)pl.tiles_a * pl.k_blocks * (pl.grid + 1) < (1ll << 31) && (long long)pl.tiles_a * pl.tiles_b < (1ll << 31),
+                "%s: problem too large for the 32-bit tile scheduler (M=%d N=%d K=%d)", fn, M, N, K);
   if (tp != nullptr) {
     LIA_CHECK_ARG(tp->world >= 2 && tp->world <= LIA_TP_MAX_WORLD && tp->rank >= 0 && tp->rank < tp->world,
                   "%s: bad rank/world %d/%d", fn, tp->rank, tp->world);
@@ -995,6 +1137,15 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
     if (!pl.swap) {
       const char* base = reinterpret_cast<const char*>(tp->arena[tp->rank]);
       LIA_CHECK_ARG(reinterpret_cast<const char*>(out) == base + tp->out_off, "%s: for M > 128 `out` must live in the arena at out_off", fn);
+    }
+    {
+      const char* e1 = getenv("LIA_TP_LATE_TRIGGER");
+      const char* e2 = getenv("LIA_TP_POLL_BACKOFF");
+      const char* e3 = getenv("LIA_TP_NO_WAIT");
+      const char* e4 = getenv("LIA_TP_NO_PUSH");
+      const char* e5 = getenv("LIA_TP_OPTS");        // raw probe bits (16: skip the exit accounting)
+      if (e5) ep.tp.opts |= atoi(e5);
+      ep.tp.opts |= ((e1 && atoi(e1)) ? 1 : 0) | ((e2 && atoi(e2)) ? 2 : 0) | ((e3 && atoi(e3)) ? 4 : 0) | ((e4 && atoi(e4)) ? 8 : 0);
     }
     ep.tp.rank = tp->rank;
     ep.tp.world = tp->world;
@@ -1047,7 +1198,7 @@ extern "C" size_t lia_tp_ctl_bytes(void) {
 extern "C" size_t lia_tp_recv_bytes(int M, int N, int K, int world) {
   if (M <= 0 || N <= 0 || K <= 0 || world <= 0) return 0;
   const Plan pl = make_plan(M, N, K);
-  if (pl.swap) return (size_t)world * pl.bn * N * sizeof(bf16);                       // [src][bn rows][N]
+  if (pl.swap) return (size_t)world * pl.bn * N * sizeof(bf16) * 2;                   // [src][bn rows][N] in {data, epoch} words
   const size_t units = (size_t)pl.tiles_a * pl.tiles_b;
   return ((units + world - 1) / world) * world * (size_t)(TILE_A * pl.bn) * sizeof(bf16);   // [owned tile][src][128][bn]
 }

@@ -24,6 +24,7 @@ Policy mapping: 0/2/3/4 -> all-GPU compute; 1 (full CPU, the IPEX
 baseline) is not part of this build -- ``bench.py --impl reference`` times it.
 """
 import math
+import os
 import time
 from dataclasses import dataclass, field
 
@@ -108,6 +109,8 @@ class _Workspace:
         self.arena = arena          # tp.PeerArena: row-parallel projections run fused with their all-reduce
         self.ln, self.q, self.ctx, self.ffn = e(rows, h), e(rows, hq), e(rows, hq), e(rows, fq)
         self.x1 = arena.tensor("x1", (rows, h)) if arena is not None else e(rows, h)
+        # decode (M <= 128) needs no remotely writable output: keep its residual stream out of the peer-mapped arena
+        self.x1d = e(batch, h) if (arena is not None and os.environ.get("LIA_TP_DECODE_ARENA", "0") == "0") else self.x1
         self.tp = e(rows, h) if layout.tp > 1 and arena is None else None
         shapes = []
         for m in {rows, batch}:
@@ -139,10 +142,15 @@ class _GenState:
             # result straight into every rank's copy (include/lia_b200.h, lia_gemm_allreduce_bf16)
             lay, lib = model.layout, _lib.load()
             recv = max(lib.lia_tp_recv_bytes(m, h, k, model.tp_world) for m in {mb * S, B} for k in (lay.hq, lay.fq))
+            loop = os.environ.get("LIA_TP_SELF_LOOP", "0") != "0"      # timing probe: one process, peers = itself
             self.arena = tp_mod.PeerArena(model.tp_rank, model.tp_world, dev, recv,
-                                          [("x", B * S * h * 2), ("xd", B * h * 2), ("x1", rows * h * 2)])
+                                          [("x", B * S * h * 2), ("xd", B * h * 2), ("x1", rows * h * 2)],
+                                          exchange=(lambda mine: [0] * model.tp_world) if loop else None)
+            if loop:
+                self.arena.peers = [self.arena.local] * model.tp_world
             self.x = self.arena.tensor("x", (B * S, h))
-            self.xd = self.arena.tensor("xd", (B, h))
+            self.xd = (self.arena.tensor("xd", (B, h)) if os.environ.get("LIA_TP_DECODE_ARENA", "0") != "0"
+                       else torch.empty(B, h, dtype=BF16, device=dev))
         else:
             self.x = torch.empty(B * S, h, dtype=BF16, device=dev)
             self.xd = torch.empty(B, h, dtype=BF16, device=dev)
@@ -291,7 +299,8 @@ class OPTDecoder:
     # ---- one layer over a block of token rows (rows are [b-major, S] and updated in place)
     def layer_rows(self, v, rows, kc, vc, nb, S, pos0, b0, ws):
         M = nb * S
-        ln, q, ctx, x1, ffn = ws.ln[:M], ws.q[:M], ws.ctx[:M], ws.x1[:M], ws.ffn[:M]
+        ln, q, ctx, ffn = ws.ln[:M], ws.q[:M], ws.ctx[:M], ws.ffn[:M]
+        x1 = ws.x1[:M] if M > 128 else ws.x1d[:M]
         ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                   # decoder.py:204
         ops.gemm(ln, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                                        # attentions.py:376-491
                  qkv=ops.qkv_args(q, kc, vc, S, pos0, b0, self.scaling), workspace=ws.gemm)
@@ -530,7 +539,7 @@ class OPTForCausalLM:
         out_dev = torch.cat([st.prompt, st.steps_tok[:new].t()], dim=1)
         out = out_dev.to(input_ids.device)                                               # D2H of the result (syncs)
         torch.cuda.synchronize(self.device)
-        if st.arena is not None:
+        if st.arena is not None and os.environ.get("LIA_TP_SELF_LOOP", "0") == "0":
             st.arena.check()                          # a peer that never showed up: raise instead of returning garbage
         lat = [ev[i].elapsed_time(ev[i + 1]) / 1e3 for i in range(new)]
         self.last_timing = {"prefill_s": lat[0], "decode_s": lat[1:], "total_s": sum(lat)}

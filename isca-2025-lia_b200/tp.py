@@ -49,7 +49,7 @@ def world_size():
 
 def all_reduce(t):
     """In-place sum over the tensor-parallel group (bf16, like the reference's message dtype)."""
-    if dist.is_initialized() and dist.get_world_size(_group) > 1:
+    if dist.is_initialized() and dist.get_world_size(_group) > 1 and os.environ.get("LIA_TP_NO_WAIT", "0") == "0":
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=_group)
     return t
 

@@ -27,7 +27,7 @@ def run(M, N, K, epi, label, n=12):
     seq += n
     torch.cuda.synchronize()
     ptr = cdll.lia_debug_gemm_trace()
-    t = np.ctypeslib.as_array(ptr, shape=(64 * 1024 * 8,)).reshape(64, 1024, 8).astype(np.int64)
+    t = np.ctypeslib.as_array(ptr, shape=(64 * 512 * 16,)).reshape(64, 512, 16).astype(np.int64)
     print(f"--- {label} M={M} N={N} K={K}: event time {e0.elapsed_time(e1)*1e3/n:.1f} us/launch")
     prev_exit = None
     for i in range(first, first + n):

@@ -108,11 +108,15 @@ def main():
             if s_.arena is not None:
                 s_.arena.close()
         m._states.clear()
-        del m
+        del m, st, toks
     dist.barrier()
+    torch.cuda.synchronize()
     if rank == 0:
         print("TP_WORKER_OK", flush=True)
-    dist.destroy_process_group()
+    sys.stdout.flush()
+    # CUDA graphs that captured NCCL kernels may still be alive in garbage: tearing the communicator down
+    # under them can block, so leave without the orderly destroy (the work is done and checked)
+    os._exit(0)
 
 
 if __name__ == "__main__":
