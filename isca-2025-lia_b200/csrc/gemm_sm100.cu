@@ -328,6 +328,120 @@ __device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
   }
 }
 
+// Fused all-reduce, decode shapes, world >= 4: second half of the exchange (see the call site).  Kept out of line so
+// that the plain projections -- which share this kernel image -- pay neither its registers nor its instruction bytes.
+template <int BN>
+__device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* rb, int epoch, int parity, int* tp_err, int ta,
+                                              int m0, int n_col, int rows) {
+  constexpr int ITERS = BN / 8;
+  const TpDev& tp = p.tp;
+  // ---- two-shot (world >= 4).  Ownership is per (row group, tile): the 8 values of row m = m0 + 8*it of
+  // tile ta are reduced by rank (it + ta) % world, so EVERY thread of EVERY CTA on every rank reduces 1/world
+  // of its own values (all `world` partials in flight at once: one L2 round trip) and receives the rest as
+  // finals (all in flight at once: one more round trip) -- two one-way NVLink latencies per exchange,
+  // 2(world-1)/world x the data per rank, and no CTA idles while a few "owner" CTAs reduce whole tiles.
+  const size_t final_base = ((size_t)tp.world * BN * p.N) >> 2;   // finals follow the `world` partial slots
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
+  auto give_up = [&]() -> bool {                 // a peer that never shows up must not hang the GPU
+    if (tp.opts & 4) return true;                // timing probe only: do not wait (results are garbage)
+    if ((++spins & 255u) != 0) return false;
+    if (*reinterpret_cast<volatile int*>(tp_err) != 0) return true;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    if (t0 == 0) t0 = t;
+    else if (t - t0 > TP_TIMEOUT_NS) {
+      atomicExch(tp_err, 1);
+      return true;
+    }
+    return false;
+  };
+#pragma unroll 1
+  for (int it = 0; it < ITERS; ++it) {           // rows this rank reduces
+    const int m = m0 + it * 8;
+    if (m >= rows) break;
+    if ((it + ta) % tp.world != tp.rank) continue;
+    const uint4 rsel = ldg_stream(p.residual + (size_t)m * p.N + n_col);   // in flight while the partials are polled
+    const uint4* q0 = rb + (((size_t)m * p.N + n_col) >> 2);
+    const size_t src_stride = ((size_t)BN * p.N) >> 2;
+    float sum[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = 0.f;
+    constexpr int SH = LIA_TP_MAX_WORLD / 2;     // partials in flight per poll (keeps the caller spill-free)
+#pragma unroll 1
+    for (int s0 = 0; s0 < tp.world; s0 += SH) {
+      uint4 lo[SH], hi[SH];
+      bool ok;
+      do {
+        ok = true;
+#pragma unroll
+        for (int k = 0; k < SH; ++k)
+          if (s0 + k < tp.world) {
+            lo[k] = ld_volatile_v4(q0 + (s0 + k) * src_stride);
+            hi[k] = ld_volatile_v4(q0 + (s0 + k) * src_stride + 1);
+          }
+#pragma unroll
+        for (int k = 0; k < SH; ++k)
+          if (s0 + k < tp.world)
+            ok = ok && lo[k].y == (uint32_t)epoch && lo[k].w == (uint32_t)epoch && hi[k].y == (uint32_t)epoch &&
+                 hi[k].w == (uint32_t)epoch;
+      } while (!ok && !give_up());
+#pragma unroll
+      for (int k = 0; k < SH; ++k)
+        if (s0 + k < tp.world) {                 // rank order, fp32: bit-identical on every rank
+          float g[8];
+          unpack_bf16x2(lo[k].x, g[0], g[1]);
+          unpack_bf16x2(lo[k].z, g[2], g[3]);
+          unpack_bf16x2(hi[k].x, g[4], g[5]);
+          unpack_bf16x2(hi[k].z, g[6], g[7]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sum[i] += g[i];
+        }
+    }
+    float r[8];
+    unpack8(rsel, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum[i] = r[i] + bf16r(sum[i]);
+    const uint4 o = pack8(sum);
+    const uint4 flo = make_uint4(o.x, (uint32_t)epoch, o.y, (uint32_t)epoch);
+    const uint4 fhi = make_uint4(o.z, (uint32_t)epoch, o.w, (uint32_t)epoch);
+    const size_t fidx = final_base + (((size_t)m * p.N + n_col) >> 2);
+    for (int r2 = 0; r2 < tp.world; ++r2) {      // second shot: finals to every peer, framed like the partials
+      if (r2 == tp.rank || (tp.opts & 8)) continue;
+      uint4* dst = reinterpret_cast<uint4*>(tp.recv(r2, parity)) + fidx;
+      st_volatile_v4(dst, flo);
+      st_volatile_v4(dst + 1, fhi);
+    }
+    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = o;
+  }
+  constexpr int RG = ITERS < 4 ? ITERS : 4;      // rows other ranks reduce: their finals, RG rows in flight
+#pragma unroll 1
+  for (int it0 = 0; it0 < ITERS; it0 += RG) {
+    uint4 lo[RG], hi[RG];
+    bool ok;
+    do {
+      ok = true;
+#pragma unroll
+      for (int j = 0; j < RG; ++j) {
+        const int m = m0 + (it0 + j) * 8;
+        if (m < rows && (it0 + j + ta) % tp.world != tp.rank) {
+          const uint4* q = rb + final_base + (((size_t)m * p.N + n_col) >> 2);
+          lo[j] = ld_volatile_v4(q);
+          hi[j] = ld_volatile_v4(q + 1);
+          ok = ok && lo[j].y == (uint32_t)epoch && lo[j].w == (uint32_t)epoch && hi[j].y == (uint32_t)epoch &&
+               hi[j].w == (uint32_t)epoch;
+        }
+      }
+    } while (!ok && !give_up());
+#pragma unroll
+    for (int j = 0; j < RG; ++j) {
+      const int m = m0 + (it0 + j) * 8;
+      if (m < rows && (it0 + j + ta) % tp.world != tp.rank)
+        *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = make_uint4(lo[j].x, lo[j].z, hi[j].x, hi[j].z);
+    }
+  }
+}
+
 // optional per-CTA timeline (LIA_GEMM_TRACE=1): 16 globaltimer stamps per CTA (<= 512 CTAs) in mapped host memory
 __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
   if (trace != nullptr) {
@@ -340,7 +454,8 @@ __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
 // ------------------------------------------------------------------ the kernel
 template <bool SWAP, int BN, int STAGES, bool TP>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, EpiParams p,
+lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const __grid_constant__ EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
                         int* __restrict__ flags, unsigned long long* __restrict__ trace) {
   using L = SmemLayout<SWAP, BN, STAGES>;
@@ -585,10 +700,11 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint4 resv[ITERS];
       if (SWAP && w.kb0 == 0 && n_ok) {
         epilogue_load_bias8(p, n_col, biasf);
+        const bool need_res = !(tp_on && (tp.opts & 128));   // two-shot: only the reducing rank of a row reads its residual
 #pragma unroll
         for (int it = 0; it < ITERS; ++it) {
           const int m = m0 + it * 8;
-          resv[it] = (m < rows) ? epilogue_load_residual8(p, m, n_col) : make_uint4(0, 0, 0, 0);
+          resv[it] = (m < rows && need_res) ? epilogue_load_residual8(p, m, n_col) : make_uint4(0, 0, 0, 0);
         }
       }
       mbar_wait(tfull_bar(acc), acc_phase);
@@ -675,6 +791,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         float* stgf = reinterpret_cast<float*>(smem_gen + STAGES * L::STAGE_BYTES);
         const bool full = (w.kb0 == 0 && w.kb1 == k_blocks);
         const bool owner = (w.kb0 == 0);                   // first k-piece: this CTA finishes the tile
+        const bool two_shot = tp_on && (tp.opts & 128);    // fused all-reduce, world >= 4 (see the reduce side below)
         float* slot = ws + (size_t)blockIdx.x * (BN * TILE_A);
         constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -781,6 +898,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                     const size_t idx = (((size_t)tp.rank * BN + m) * p.N + n_col) >> 2;   // uint4 index: 2 per 8 values
                     for (int r2 = 0; r2 < tp.world; ++r2) {
                       if ((tp.opts & 8) && r2 != tp.rank) continue;   // timing probe only: no remote stores
+                      if (two_shot && r2 != (it0 + j + w.ta) % tp.world) continue;   // two-shot: only the row's reducing rank
                       uint4* dst = reinterpret_cast<uint4*>(tp.recv(r2, parity)) + idx;
                       st_volatile_v4(dst, lo);
                       st_volatile_v4(dst + 1, hi);
@@ -797,80 +915,84 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             if (et == 0) stamp(trace, 8);
             if (n_ok && !(tp.opts & 32)) {
               const uint4* rb = reinterpret_cast<const uint4*>(tp.recv(tp.rank, parity));
-              constexpr int RB2 = ITERS < 4 ? ITERS : 4;
-#pragma unroll 1
-              for (int it0 = 0; it0 < ITERS; it0 += RB2) {
-                uint4 rcur[RB2];
-#pragma unroll
-                for (int j = 0; j < RB2; ++j) {
-                  rcur[j] = resv[j];
-#pragma unroll
-                  for (int b = 1; b < ITERS / RB2; ++b)
-                    if (it0 == b * RB2) rcur[j] = resv[b * RB2 + j];
-                }
-                float sum[RB2][8];
-#pragma unroll
-                for (int j = 0; j < RB2; ++j)
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) sum[j][i] = 0.f;
-                for (int src = 0; src < tp.world; ++src) {
-                  uint4 lo[RB2], hi[RB2];
-                  unsigned long long t0 = 0;
-                  unsigned spins = 0;
-                  bool ok;
-                  do {
-                    ok = true;
-#pragma unroll
-                    for (int j = 0; j < RB2; ++j) {
-                      const int m = m0 + (it0 + j) * 8;
-                      if (m < rows) {
-                        const uint4* q = rb + ((((size_t)src * BN + m) * p.N + n_col) >> 2);
-                        lo[j] = ld_volatile_v4(q);
-                        hi[j] = ld_volatile_v4(q + 1);
-                      }
-                    }
-#pragma unroll
-                    for (int j = 0; j < RB2; ++j) {
-                      const int m = m0 + (it0 + j) * 8;
-                      if (m < rows)
-                        ok = ok && lo[j].y == (uint32_t)epoch && lo[j].w == (uint32_t)epoch && hi[j].y == (uint32_t)epoch &&
-                             hi[j].w == (uint32_t)epoch;
-                    }
-                    if (tp.opts & 4) ok = true;               // timing probe only: do not wait for the peer (results are garbage)
-                    if (!ok && (tp.opts & 2)) __nanosleep(100);
-                    if (!ok && (++spins & 255u) == 0) {       // a peer that never shows up must not hang the GPU
-                      if (*reinterpret_cast<volatile int*>(tp_err) != 0) break;
-                      unsigned long long t;
-                      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
-                      if (t0 == 0) t0 = t;
-                      else if (t - t0 > TP_TIMEOUT_NS) {
-                        atomicExch(tp_err, 1);
-                        break;
-                      }
-                    }
-                  } while (!ok);
-#pragma unroll
+              if (!two_shot) {
+                constexpr int RB2 = ITERS < 4 ? ITERS : 4;
+  #pragma unroll 1
+                for (int it0 = 0; it0 < ITERS; it0 += RB2) {
+                  uint4 rcur[RB2];
+  #pragma unroll
                   for (int j = 0; j < RB2; ++j) {
-                    float g[8];
-                    unpack_bf16x2(lo[j].x, g[0], g[1]);
-                    unpack_bf16x2(lo[j].z, g[2], g[3]);
-                    unpack_bf16x2(hi[j].x, g[4], g[5]);
-                    unpack_bf16x2(hi[j].z, g[6], g[7]);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sum[j][i] += g[i];
+                    rcur[j] = resv[j];
+  #pragma unroll
+                    for (int b = 1; b < ITERS / RB2; ++b)
+                      if (it0 == b * RB2) rcur[j] = resv[b * RB2 + j];
+                  }
+                  float sum[RB2][8];
+  #pragma unroll
+                  for (int j = 0; j < RB2; ++j)
+  #pragma unroll
+                    for (int i = 0; i < 8; ++i) sum[j][i] = 0.f;
+                  for (int src = 0; src < tp.world; ++src) {
+                    uint4 lo[RB2], hi[RB2];
+                    unsigned long long t0 = 0;
+                    unsigned spins = 0;
+                    bool ok;
+                    do {
+                      ok = true;
+  #pragma unroll
+                      for (int j = 0; j < RB2; ++j) {
+                        const int m = m0 + (it0 + j) * 8;
+                        if (m < rows) {
+                          const uint4* q = rb + ((((size_t)src * BN + m) * p.N + n_col) >> 2);
+                          lo[j] = ld_volatile_v4(q);
+                          hi[j] = ld_volatile_v4(q + 1);
+                        }
+                      }
+  #pragma unroll
+                      for (int j = 0; j < RB2; ++j) {
+                        const int m = m0 + (it0 + j) * 8;
+                        if (m < rows)
+                          ok = ok && lo[j].y == (uint32_t)epoch && lo[j].w == (uint32_t)epoch && hi[j].y == (uint32_t)epoch &&
+                               hi[j].w == (uint32_t)epoch;
+                      }
+                      if (tp.opts & 4) ok = true;               // timing probe only: do not wait for the peer (results are garbage)
+                      if (!ok && (tp.opts & 2)) __nanosleep(100);
+                      if (!ok && (++spins & 255u) == 0) {       // a peer that never shows up must not hang the GPU
+                        if (*reinterpret_cast<volatile int*>(tp_err) != 0) break;
+                        unsigned long long t;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+                        if (t0 == 0) t0 = t;
+                        else if (t - t0 > TP_TIMEOUT_NS) {
+                          atomicExch(tp_err, 1);
+                          break;
+                        }
+                      }
+                    } while (!ok);
+  #pragma unroll
+                    for (int j = 0; j < RB2; ++j) {
+                      float g[8];
+                      unpack_bf16x2(lo[j].x, g[0], g[1]);
+                      unpack_bf16x2(lo[j].z, g[2], g[3]);
+                      unpack_bf16x2(hi[j].x, g[4], g[5]);
+                      unpack_bf16x2(hi[j].z, g[6], g[7]);
+  #pragma unroll
+                      for (int i = 0; i < 8; ++i) sum[j][i] += g[i];
+                    }
+                  }
+  #pragma unroll
+                  for (int j = 0; j < RB2; ++j) {
+                    const int m = m0 + (it0 + j) * 8;
+                    if (m < rows) {
+                      float r[8];
+                      unpack8(rcur[j], r);
+  #pragma unroll
+                      for (int i = 0; i < 8; ++i) sum[j][i] = r[i] + bf16r(sum[j][i]);
+                      *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = pack8(sum[j]);
+                    }
                   }
                 }
-#pragma unroll
-                for (int j = 0; j < RB2; ++j) {
-                  const int m = m0 + (it0 + j) * 8;
-                  if (m < rows) {
-                    float r[8];
-                    unpack8(rcur[j], r);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) sum[j][i] = r[i] + bf16r(sum[j][i]);
-                    *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = pack8(sum[j]);
-                  }
-                }
+              } else {
+                tp_two_shot_rows<BN>(p, rb, epoch, parity, tp_err, w.ta, m0, n_col, rows);
               }
             }
             if (et == 0) stamp(trace, 11);
@@ -1145,6 +1267,10 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
       const char* e4 = getenv("LIA_TP_NO_PUSH");
       const char* e5 = getenv("LIA_TP_OPTS");        // raw probe bits (16: skip the exit accounting)
       if (e5) ep.tp.opts |= atoi(e5);
+      // decode (M <= 128): one-shot costs (world-1) x the data per rank and one NVLink hop, two-shot 2(world-1)/world x
+      // and two hops -- measured cross-over between world 2 and 4
+      const char* e6 = getenv("LIA_TP_DECODE_TWOSHOT");
+      if (pl.swap && (e6 ? atoi(e6) != 0 : tp->world >= 4)) ep.tp.opts |= 128;
       ep.tp.opts |= ((e1 && atoi(e1)) ? 1 : 0) | ((e2 && atoi(e2)) ? 2 : 0) | ((e3 && atoi(e3)) ? 4 : 0) | ((e4 && atoi(e4)) ? 8 : 0);
     }
     ep.tp.rank = tp->rank;
@@ -1198,7 +1324,7 @@ extern "C" size_t lia_tp_ctl_bytes(void) {
 extern "C" size_t lia_tp_recv_bytes(int M, int N, int K, int world) {
   if (M <= 0 || N <= 0 || K <= 0 || world <= 0) return 0;
   const Plan pl = make_plan(M, N, K);
-  if (pl.swap) return (size_t)world * pl.bn * N * sizeof(bf16) * 2;                   // [src][bn rows][N] in {data, epoch} words
+  if (pl.swap) return (size_t)(world + 1) * pl.bn * N * sizeof(bf16) * 2;             // [src][bn rows][N] partials + [bn][N] finals, {data, epoch} words
   const size_t units = (size_t)pl.tiles_a * pl.tiles_b;
   return ((units + world - 1) / world) * world * (size_t)(TILE_A * pl.bn) * sizeof(bf16);   // [owned tile][src][128][bn]
 }

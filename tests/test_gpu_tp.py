@@ -30,11 +30,17 @@ def _ref(As, Ws, bs, res):
     return (res.float() + tot.to(BF16).float()).to(BF16)
 
 
-@pytest.mark.parametrize("world,M,N,K", [(2, 8, 256, 512), (2, 64, 1024, 1536), (4, 64, 512, 256),
-                                         (2, 384, 512, 256), (2, 1000, 768, 320), (4, 512, 1024, 128)])
-def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, monkeypatch):
+@pytest.mark.parametrize("world,M,N,K,twoshot", [
+    (2, 8, 256, 512, None), (2, 64, 1024, 1536, None), (4, 64, 512, 256, "0"),
+    # decode two-shot (default for world >= 4): tile ta is reduced by rank ta % world, finals pushed to all
+    (4, 64, 512, 256, None), (2, 64, 1024, 1536, "1"), (4, 24, 1280, 192, None), (8, 64, 2048, 128, None),
+    (8, 128, 1024, 512, None), (3, 40, 640, 320, "1"),
+    (2, 384, 512, 256, None), (2, 1000, 768, 320, None), (4, 512, 1024, 128, None)])
+def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, twoshot, monkeypatch):
     if not torch.cuda.is_available():
         pytest.skip("needs a GPU")
+    if twoshot is not None:
+        monkeypatch.setenv("LIA_TP_DECODE_TWOSHOT", twoshot)
     import lia_b200  # noqa: F401
     from lia_b200 import _lib, ops, tp
     lib = _lib.load()
