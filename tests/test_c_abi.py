@@ -44,8 +44,9 @@ def test_abi_version_and_struct_layout(built):
     # LiaTpArgs: 2 int32 + 8 pointers + 4 uint64
     assert ctypes.sizeof(built.LiaTpArgs) == 8 + 64 + 32 and built.LiaTpArgs.ctl_off.offset == 72
     assert lib.lia_tp_ctl_bytes() == (64 + 16384 * 8 + 16384) * 4
-    # receive area: one-shot [world][bn][N] {bf16x2, epoch} words for M <= 128, two-shot [owned tiles][world][128][bn] above
-    assert lib.lia_tp_recv_bytes(64, 7168, 896, 8) == 8 * 64 * 7168 * 2 * 2
+    # receive area for M <= 128: [world][bn][N] partials + [bn][N] two-shot finals as {bf16x2, epoch} words;
+    # above: two-shot [owned tiles][world][128][bn]
+    assert lib.lia_tp_recv_bytes(64, 7168, 896, 8) == (8 + 1) * 64 * 7168 * 2 * 2
     assert lib.lia_tp_recv_bytes(8192, 7168, 896, 8) == (64 * 28 // 8) * 8 * 128 * 256 * 2
     tpargs = built.LiaTpArgs()
     rc = lib.lia_gemm_allreduce_bf16(16, 16, None, 16, 16, 8, 16, 16, ctypes.byref(tpargs), None, 0, None)
