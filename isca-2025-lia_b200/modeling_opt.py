@@ -245,6 +245,21 @@ class OPTDecoder:
     def load_layers(self, layer_fn, gpu_percentage=100):
         """``layer_fn(i, device)`` -> full layer dict on ``device``; resident layers are packed on the
         GPU, the rest straight into the pinned host arena."""
+        def fill(i, out):
+            w = layer_fn(i, self.device)
+            if out.device.type == "cpu":
+                out.copy_(pack_layer(w, self.layout, self.tp_rank))
+            else:
+                pack_layer(w, self.layout, self.tp_rank, out=out)
+        self._place(fill, gpu_percentage, host_fill=False)
+
+    def load_packed(self, read_slab, gpu_percentage=100):
+        """``read_slab(i, out)`` fills ``out`` -- a flat CPU bf16 tensor of ``layout.numel`` elements -- with
+        this rank's already-packed slab of layer i (checkpoint.SlabCheckpoint.read_slab).  Streamed layers are
+        read straight into the pinned arena; resident ones go through one pinned staging slab."""
+        self._place(read_slab, gpu_percentage, host_fill=True)
+
+    def _place(self, fill, gpu_percentage, host_fill):
         L = self.config.num_hidden_layers
         n_res = L if gpu_percentage >= 100 else int(L * gpu_percentage / 100)   # M:1182 (100 == intended "all")
         self.n_resident = n_res
@@ -255,16 +270,25 @@ class OPTDecoder:
         n_host = L - n_res
         if n_host:
             self.host_arena = HostArena(self.layout.numel * n_host)
+        stage = HostArena(self.layout.numel) if (host_fill and n_res) else None
         for i in range(L):
             if i < n_res:
-                slab = pack_layer(layer_fn(i, self.device), self.layout, self.tp_rank)
+                slab = torch.empty(self.layout.numel, dtype=BF16, device=self.device)
+                if host_fill:
+                    fill(i, stage.tensor)
+                    slab.copy_(stage.tensor)                 # synchronous w.r.t. the host: staging is reusable
+                else:
+                    fill(i, slab)
                 self.resident.append(slab)
                 self.resident_views.append(self.layout.views(slab))
             else:
                 j = i - n_res
                 dst = self.host_arena.tensor[j * self.layout.numel:(j + 1) * self.layout.numel]
-                dst.copy_(pack_layer(layer_fn(i, self.device), self.layout, self.tp_rank))
+                fill(i, dst)
                 self.host_slabs.append(dst)
+        if stage is not None:
+            torch.cuda.synchronize(self.device)
+            stage.close()
         if n_host:
             torch.cuda.synchronize(self.device)
             self.streamer = LayerStreamer(self.layout, self.host_slabs, self.device)
@@ -429,6 +453,29 @@ class OPTForCausalLM:
         dec.load_layers(lambda i, dev: {k: t.to(dev, BF16) for k, t in layer_from_hf_state_dict(sd, i).items()},
                         gpu_percentage)
         return self
+
+    @classmethod
+    def from_pretrained(cls, path, device="cuda", gpu_percentage=100, tp_rank=0, tp_world=1, config=None, **unused):
+        """Load a checkpoint directory (run_generation.py:159-167 ``from_pretrained``): either an HF OPT
+        checkpoint (safetensors or pytorch_model.bin, sharded or not -- the form utils/opt-weight-gen.py:66-69
+        writes) or this build's native slab directory (checkpoint.py), whose layers are read straight into
+        HBM / the pinned arena without repacking."""
+        from . import checkpoint
+        ck = checkpoint.open_checkpoint(path)
+        cfg = config or ck.config
+        native = isinstance(ck, checkpoint.SlabCheckpoint)
+        if native and ck.tp_world != tp_world:
+            raise ValueError(f"{path} holds slabs for tensor-parallel world {ck.tp_world}, not {tp_world}; "
+                             "re-run checkpoint.convert(..., tp_world=)")
+        m = cls(cfg, device, tp_rank=tp_rank, tp_world=tp_world)
+        dec = m.model.decoder
+        dec.load_embeddings(ck.embeddings())
+        if native:
+            dec.load_packed(lambda i, out: ck.read_slab(i, tp_rank, out), gpu_percentage)
+            ck.close()
+        else:
+            dec.load_layers(lambda i, dev: ck.layer(i, dev), gpu_percentage)
+        return m
 
     def eval(self):
         return self

@@ -67,14 +67,27 @@ def main(argv=None):
     rank, world = tp.init_from_env()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
-    cfg = get_config(args.model_id)
-    if args.num_layers:
-        cfg.num_hidden_layers = args.num_layers
-    cfg.token_latency = bool(args.token_latency)
     S = int(args.input_tokens)
-    cfg.text_max_length = S + args.max_new_tokens                     # run_generation.py:149
-    model = lia_b200.OPTForCausalLM(cfg, torch.device("cuda", local), tp_rank=rank, tp_world=world)
-    model.init_weights(seed=args.seed, kind="dummy" if args.dummy_weights else "normal", gpu_percentage=args.gpu_percentage)
+    dev = torch.device("cuda", local)
+    if os.path.isdir(args.model_id):
+        # a checkpoint directory (HF safetensors / pytorch_model.bin, or native slabs): run_generation.py:159-167
+        from lia_b200 import checkpoint
+        cfg = checkpoint.open_checkpoint(args.model_id).config
+        if args.num_layers:
+            cfg.num_hidden_layers = args.num_layers
+        cfg.token_latency = bool(args.token_latency)
+        cfg.text_max_length = S + args.max_new_tokens                 # run_generation.py:149
+        model = lia_b200.OPTForCausalLM.from_pretrained(args.model_id, dev, gpu_percentage=args.gpu_percentage,
+                                                        tp_rank=rank, tp_world=world, config=cfg)
+    else:
+        cfg = get_config(args.model_id)
+        if args.num_layers:
+            cfg.num_hidden_layers = args.num_layers
+        cfg.token_latency = bool(args.token_latency)
+        cfg.text_max_length = S + args.max_new_tokens                 # run_generation.py:149
+        model = lia_b200.OPTForCausalLM(cfg, dev, tp_rank=rank, tp_world=world)
+        model.init_weights(seed=args.seed, kind="dummy" if args.dummy_weights else "normal",
+                           gpu_percentage=args.gpu_percentage)
     g = torch.Generator().manual_seed(1234)
     prompt = torch.randint(3, cfg.vocab_size, (1, S), generator=g)
     input_ids = prompt.expand(args.batch_size, S).contiguous().pin_memory()       # run_generation.py:285

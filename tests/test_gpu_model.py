@@ -95,6 +95,39 @@ def test_tiny_model_tokens_match_stock_transformers(lia, golden_dir):
         assert np.array_equal(toks.numpy(), z["tokens"]), rep
 
 
+def test_from_pretrained_checkpoint_forms(lia, golden_dir, tmp_path):
+    """from_pretrained (run_generation.py:159-167) over an HF safetensors directory and over this build's native
+    slab directory, resident and streamed: same bits in HBM as load_state_dict, same tokens as stock transformers."""
+    from lia_b200 import checkpoint
+    z = np.load(os.path.join(golden_dir, "model_hf_tiny.npz"))
+    sd = {k[3:]: _bf16(z[k]) for k in z.files if k.startswith("sd:")}
+    h, L, H, V, P = (int(z[k]) for k in ("h", "L", "H", "V", "P"))
+    hf = tmp_path / "hf"
+    hf.mkdir()
+    checkpoint.write_safetensors(str(hf / "model.safetensors"), sd)
+    import json
+    json.dump({"model_type": "opt", "hidden_size": h, "num_hidden_layers": L, "num_attention_heads": H, "ffn_dim": 4 * h,
+               "vocab_size": V, "max_position_embeddings": P, "word_embed_proj_dim": h}, open(hf / "config.json", "w"))
+    checkpoint.convert(str(hf), str(tmp_path / "slabs"))
+    ids = torch.from_numpy(z["input_ids"])
+    new = int(z["new"])
+    base = lia.OPTForCausalLM(lia.OPTConfig(hidden_size=h, num_hidden_layers=L, num_attention_heads=H, ffn_dim=4 * h, vocab_size=V,
+                                            max_position_embeddings=P), "cuda").load_state_dict(sd)
+    for d in ("hf", "slabs"):
+        for pct in (100, 0):
+            m = lia.OPTForCausalLM.from_pretrained(str(tmp_path / d), "cuda", gpu_percentage=pct)
+            dec = m.model.decoder
+            assert dec.n_resident == (L if pct == 100 else 0)
+            for i in range(L):
+                got = dec.resident[i] if pct == 100 else dec.host_slabs[i]
+                assert torch.equal(got.cpu(), base.model.decoder.resident[i].cpu()), (d, pct, i)
+            toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new, gpu_percentage=pct)
+            assert np.array_equal(toks.numpy(), z["tokens"]), (d, pct)
+            del m
+    with pytest.raises(ValueError, match="tensor-parallel world"):
+        lia.OPTForCausalLM.from_pretrained(str(tmp_path / "slabs"), "cuda", tp_rank=0, tp_world=2)
+
+
 def _oracle_model(m, device):
     """Unpack a lia_b200 model's slabs into the oracle's dict format (same bits)."""
     dec = m.model.decoder
