@@ -32,6 +32,7 @@ import torch
 
 from . import _lib, ops, tp as tp_mod
 from .ops import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV
+from .kv_spill import KVSpill, plan_resident_layers
 from .streamer import HostArena, LayerStreamer
 from .weights import LAYER_KEYS, LayerLayout, layer_from_hf_state_dict, pack_layer, random_embeddings, random_layer
 
@@ -128,8 +129,6 @@ class _GenState:
         Hl = cfg.num_attention_heads // model.tp_world
         self.B, self.S, self.new = B, S, new
         self.Tmax = S + new
-        self.kc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) for _ in range(L)]
-        self.vc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) for _ in range(L)]
         self.beam_idx = torch.zeros(self.Tmax, B, dtype=torch.long, device=dev)
         self.prompt = torch.zeros(B, S, dtype=torch.int64, device=dev)
         self.steps_tok = torch.zeros(max(new, 1), B, dtype=torch.int64, device=dev)
@@ -159,10 +158,40 @@ class _GenState:
         self.ws = _Workspace(cfg, model.layout, rows, B, dev, self.arena)
         self.graphs = {}
         self.calls = 0
+        # KV cache last, once everything else of this shape is placed: layers whose K/V do not fit in HBM are
+        # spilled to pinned host memory (kv_spill.py; lia/modeling_opt.py:326-349 keeps the whole cache there)
+        per_layer = 2 * self.Tmax * B * Hl * d * 2
+        n_res = model.kv_resident_layers
+        if n_res is None and os.environ.get("LIA_KV_RESIDENT_LAYERS"):
+            n_res = int(os.environ["LIA_KV_RESIDENT_LAYERS"])
+        if n_res is None:
+            if dev.type == "cuda":
+                torch.cuda.empty_cache()
+                free = torch.cuda.mem_get_info(dev)[0]
+            else:
+                free = L * per_layer + (8 << 30)
+            n_res = plan_resident_layers(L, per_layer, free)
+        n_res = max(0, min(L, int(n_res)))
+        self.kv_resident = n_res
+        self.kc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) if i < n_res else None for i in range(L)]
+        self.vc = [torch.zeros(self.Tmax, B, Hl, d, dtype=BF16, device=dev) if i < n_res else None for i in range(L)]
+        self.spill = KVSpill(L - n_res, self.Tmax, B, Hl, d, dev) if n_res < L else None
 
     def past_key_values(self, T):
+        """The reference's per-layer 4-tuple; a spilled layer's K/V are its pinned host tensors (where the
+        reference keeps every layer's, M:1383-1388)."""
         marker = torch.empty(1, T, T, 1, dtype=torch.long, device="meta")   # only .shape is ever read (M:1111)
-        return tuple((marker, k, v, self.beam_idx) for k, v in zip(self.kc, self.vc))
+        ks = [k if k is not None else self.spill.host_k[i - self.kv_resident] for i, k in enumerate(self.kc)]
+        vs = [v if v is not None else self.spill.host_v[i - self.kv_resident] for i, v in enumerate(self.vc)]
+        return tuple((marker, k, v, self.beam_idx) for k, v in zip(ks, vs))
+
+    def close(self):
+        if self.arena is not None:
+            self.arena.close()
+            self.arena = None
+        if self.spill is not None:
+            self.spill.close()
+            self.spill = None
 
 
 class OPTDecoderLayer:
@@ -355,18 +384,26 @@ class OPTDecoder:
             tp_mod.all_reduce(part)
             ops.residual_add(part, x1, out=rows)                                                      # decoder.py:317
 
-    def run_layers(self, x, kcs, vcs, B, S, pos0, num_minibatch, ws):
+    def run_layers(self, x, kcs, vcs, B, S, pos0, num_minibatch, ws, spill=None):
         """Layer-major, minibatch-minor loop (lia/modeling_opt.py:1222, 1284) with double-buffered
-        weight streaming for non-resident layers."""
+        weight streaming for non-resident layers and, where ``kcs[li] is None``, double-buffered K/V
+        of that layer from the pinned host spill (``spill``: kv_spill.KVSpill holding the last layers)."""
         mb = B if S == 1 else max(1, B // max(1, num_minibatch or 1))      # M:1178
+        L = self.config.num_hidden_layers
         if self.streamer is not None:
             self.streamer.begin()
-        for li in range(self.config.num_hidden_layers):
+        if spill is not None:
+            spill.begin(pos0)
+        for li in range(L):
             streamed = li >= self.n_resident
             v = self.streamer.acquire(li - self.n_resident) if streamed else self.resident_views[li]
+            spilled = kcs[li] is None
+            kc, vc = spill.acquire(li - (L - spill.n), pos0) if spilled else (kcs[li], vcs[li])
             for b0 in range(0, B, mb):
                 nb = min(mb, B - b0)
-                self.layer_rows(v, x[b0 * S:(b0 + nb) * S], kcs[li], vcs[li], nb, S, pos0, b0, ws)
+                self.layer_rows(v, x[b0 * S:(b0 + nb) * S], kc, vc, nb, S, pos0, b0, ws)
+            if spilled:
+                spill.release(li - (L - spill.n), pos0, S)
             if streamed:
                 self.streamer.release(li - self.n_resident)
 
@@ -429,6 +466,7 @@ class OPTForCausalLM:
         self.layout = self.model.decoder.layout
         self._states = {}
         self.use_cuda_graphs = True
+        self.kv_resident_layers = None      # None: as many layers' K/V in HBM as fit (rest spilled to pinned host)
         self.last_timing = None
 
     # ---- weights
@@ -509,11 +547,10 @@ class OPTForCausalLM:
 
     # ---- generation
     def _state(self, B, S, new, num_minibatch):
-        key = (B, S, new, num_minibatch)
+        key = (B, S, new, num_minibatch, self.kv_resident_layers)
         if key not in self._states:
             for old in self._states.values():          # one live shape at a time: caches are large
-                if old.arena is not None:
-                    old.arena.close()
+                old.close()
             self._states.clear()
             self._states[key] = _GenState(self, B, S, new, num_minibatch)
         return self._states[key]
@@ -528,7 +565,7 @@ class OPTForCausalLM:
         dec, cfg = self.model.decoder, self.config
         B, S = st.B, st.S
         ops.embed(st.prompt, dec.embed_tokens, dec.embed_positions, 0, out=st.x.view(B, S, cfg.hidden_size))
-        dec.run_layers(st.x, st.kc, st.vc, B, S, 0, num_minibatch, st.ws)
+        dec.run_layers(st.x, st.kc, st.vc, B, S, 0, num_minibatch, st.ws, st.spill)
         st.xd.copy_(st.x.view(B, S, cfg.hidden_size)[:, -1, :])                           # models.py:430 last token only
         self._head_and_pick(st, st.xd, 0, suppress)
 
@@ -538,7 +575,7 @@ class OPTForCausalLM:
         past = st.S + t - 1
         ops.embed(st.steps_tok[t - 1].view(st.B, 1), dec.embed_tokens, dec.embed_positions, past,
                   out=st.xd.view(st.B, 1, cfg.hidden_size))
-        dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws)
+        dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws, st.spill)
         self._head_and_pick(st, st.xd, t, suppress)
 
     def generate(self, input_ids, max_new_tokens=32, min_new_tokens=None, do_sample=False, num_beams=1,
@@ -564,7 +601,7 @@ class OPTForCausalLM:
         st = self._state(B, S, new, num_minibatch)
         st.calls += 1
         eos = self.config.eos_token_id
-        graphs_ok = self.use_cuda_graphs and dec.streamer is None
+        graphs_ok = self.use_cuda_graphs and dec.streamer is None and st.spill is None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(new + 1)]
         st.prompt.copy_(input_ids, non_blocking=True)                                    # H2D (pinned host -> HBM)
         ev[0].record()

@@ -132,6 +132,12 @@ def main(argv=None):
     if st is not None:
         s = st.stats()
         print("Streamed weights: %.2f GB at %.1f GB/s (pinned host -> HBM)" % (s["bytes"] / 1e9, s["gbps"]))
+    for gs in model._states.values():
+        if gs.spill is not None:
+            k = gs.spill.stats()
+            print("KV cache: %d of %d layers in HBM, %d spilled to %.2f GB of pinned host memory (%.2f GB in, %.2f GB out)"
+                  % (gs.kv_resident, cfg.num_hidden_layers, k["layers"], k["host_bytes"] / 1e9, k["h2d_bytes"] / 1e9,
+                     k["d2h_bytes"] / 1e9))
     return 0
 
 

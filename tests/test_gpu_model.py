@@ -226,6 +226,42 @@ def test_scheduling_knobs_do_not_change_results(lia):
         assert torch.equal(o, outs[0]), i + 1
 
 
+def test_kv_spill_does_not_change_results(lia):
+    """KV-cache host spill (kv_spill.py; reference load_kv_cache / store_cache / store_cache_decoding,
+    lia/modeling_opt.py:326-349) is a placement knob: tokens and the cache contents handed back through
+    past_key_values must be bit-identical whichever layers' K/V live in pinned host memory, also together
+    with weight streaming."""
+    cfg = lia.modeling_opt.get_config("opt-1.3b")
+    cfg.num_hidden_layers = 5
+    g = torch.Generator().manual_seed(11)
+    B, S, new = 8, 64, 8
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=g)
+    ref_tok = ref_kv = None
+    for pct, kv_res, nmb in [(100, None, 1), (100, 0, 1), (100, 2, 2), (100, 4, 1), (40, 1, 2), (0, 3, 1)]:
+        m = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=5, gpu_percentage=pct)
+        m.kv_resident_layers = kv_res
+        for rep in range(3):                       # state re-use across generate() calls (wrap-around prefetch)
+            tok = m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=nmb, gpu_percentage=pct,
+                             prefill_policy=0, decoding_policy=0)
+            st = next(iter(m._states.values()))
+            assert st.kv_resident == (5 if kv_res is None else kv_res) and (st.spill is None) == (kv_res is None)
+            T = S + new - 1                        # rows written: the last token's K/V is never needed
+            kv = [(p[1][:T].cpu().clone(), p[2][:T].cpu().clone()) for p in st.past_key_values(T)]
+            if ref_tok is None:
+                ref_tok, ref_kv = tok, kv
+                assert all(k.abs().sum() > 0 for k, _ in kv)
+            assert torch.equal(tok, ref_tok), (pct, kv_res, rep)
+            for li, ((k, v), (rk, rv)) in enumerate(zip(kv, ref_kv)):
+                assert torch.equal(k, rk) and torch.equal(v, rv), (pct, kv_res, rep, li)
+        if st.spill is not None:
+            s_ = st.spill.stats()
+            n_sp = 5 - kv_res
+            assert st.past_key_values(T)[4][1].device.type == "cpu" and st.past_key_values(T)[4][1].is_pinned()
+            assert s_["layers"] == n_sp and s_["d2h_bytes"] == 3 * 2 * n_sp * (S + new - 1) * st.spill.row * 2
+        del m, st
+        torch.cuda.empty_cache()
+
+
 def test_full_size_layer_properties(lia):
     """OPT-30B layer dims at the bench batch (B=64): decode output vs oracle, KV round trip, and
     batch-permutation equivariance (a size-independent property of the path)."""
