@@ -140,9 +140,13 @@ int lia_residual_add_bf16(const void* x, const void* residual, void* out, size_t
  *     out = bf16( residual + bf16( sum_r  bf16( bf16(acc_r) + bias_r ) ) )
  * (bias_r is this rank's share of the bias, i.e. bias / world, tensor_parallel.py:134; the sum over
  * ranks is taken in fp32 in rank order, so every rank produces bit-identical results).
- *   M <= 128 (decode): one-shot -- the CTA that finishes an output tile pushes it into every
- *     peer's receive area as {4 data bytes, epoch} words (data and validity arrive together: one
- *     one-way NVLink latency, no fence, no flag), then reduces the `world` partials in its own.
+ *   M <= 128 (decode), world < 4: one-shot -- the CTA that finishes an output tile pushes it into
+ *     every peer's receive area as {4 data bytes, epoch} words (data and validity arrive together:
+ *     one one-way NVLink latency, no fence, no flag), then reduces the `world` partials in its own.
+ *   M <= 128 (decode), world >= 4: two-shot with per-row ownership -- row group `it` of tile `ta` is
+ *     reduced by rank (it + ta) % world, so every thread on every rank reduces 1/world of its own
+ *     values and receives the rest as finals in the same {data, epoch} framing: two one-way
+ *     latencies, 2(world-1)/world x the data per rank instead of (world-1) x.
  *   M >  128 (prefill): two-shot -- tile u is owned by rank u % world; the other ranks push their
  *     partial to the owner, which reduces, adds the residual and writes the final tile into every
  *     rank's `out` (which therefore must live inside the arena, at the same offset on every rank);

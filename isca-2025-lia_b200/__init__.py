@@ -8,7 +8,9 @@ Layout:
   modeling_opt.py  OPTForCausalLM / OPTDecoder / OPTDecoderLayer with the LIA kwargs
   weights.py       per-layer weight slabs, random-init and dummy-weight generators
   streamer.py      pinned-host layer streaming (replaces AMX-CPU compute + CXL tiering)
-  tp.py            tensor-parallel sharding + NCCL all-reduce
+  kv_spill.py      per-layer KV-cache spill to pinned host memory (K/V larger than HBM)
+  checkpoint.py    HF safetensors/.bin reader and the native per-layer slab format
+  tp.py            tensor-parallel plumbing: peer arenas for the fused projection+all-reduce kernel, NCCL bootstrap
   run.py           the reference's run.py / run_generation.py command line
 """
 from . import _lib  # noqa: F401
