@@ -266,6 +266,7 @@ class OPTDecoder:
         self.resident = []          # flat device slabs
         self.resident_views = []
         self.host_arena = None
+        self.host_pool = 0
         self.host_slabs = []
         self.streamer = None
         self._ws = {}
@@ -297,8 +298,14 @@ class OPTDecoder:
             self.streamer.close()
             self.streamer = None
         n_host = L - n_res
+        # host RAM smaller than the streamed weights (OPT-175B: 348 GB): keep only `pool` DISTINCT streamed layers in
+        # the pinned arena and let streamed layer j alias slab j % pool -- the bytes crossing PCIe per step are
+        # unchanged, the results are not those of the full model (throughput runs on dummy weights only)
+        pool = int(os.environ.get("LIA_HOST_LAYER_POOL", "0") or 0)
+        self.host_pool = pool if 0 < pool < n_host else 0
+        n_slabs = self.host_pool or n_host
         if n_host:
-            self.host_arena = HostArena(self.layout.numel * n_host)
+            self.host_arena = HostArena(self.layout.numel * n_slabs)
         stage = HostArena(self.layout.numel) if (host_fill and n_res) else None
         for i in range(L):
             if i < n_res:
@@ -312,8 +319,10 @@ class OPTDecoder:
                 self.resident_views.append(self.layout.views(slab))
             else:
                 j = i - n_res
-                dst = self.host_arena.tensor[j * self.layout.numel:(j + 1) * self.layout.numel]
-                fill(i, dst)
+                k = j % n_slabs
+                dst = self.host_arena.tensor[k * self.layout.numel:(k + 1) * self.layout.numel]
+                if j < n_slabs:
+                    fill(i, dst)
                 self.host_slabs.append(dst)
         if stage is not None:
             torch.cuda.synchronize(self.device)

@@ -132,6 +132,10 @@ def main(argv=None):
     if st is not None:
         s = st.stats()
         print("Streamed weights: %.2f GB at %.1f GB/s (pinned host -> HBM)" % (s["bytes"] / 1e9, s["gbps"]))
+        if model.model.decoder.host_pool:
+            print("NOTE: LIA_HOST_LAYER_POOL=%d -- streamed layers alias %d distinct pinned slabs (host RAM < model); "
+                  "bytes per step are those of the full model, outputs are not" % (model.model.decoder.host_pool,
+                                                                                  model.model.decoder.host_pool))
     for gs in model._states.values():
         if gs.spill is not None:
             k = gs.spill.stats()
