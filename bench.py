@@ -160,7 +160,9 @@ def _main(args, json_out):
     B, S, new = args.batch_size, args.input_tokens, args.max_new_tokens
     workload = (f"{cfg.name} bf16 random-init, {'fully HBM-resident' if args.gpu_percentage >= 100 else f'gpu-percentage {args.gpu_percentage}, rest streamed from pinned host'}, "
                 f"batch {B}, input {S}, max-new-tokens {new}, num-minibatch {args.num_minibatch}"
-                + (f" [DEBUG depth {args.layers}: not the headline config]" if args.layers else " (BASELINE.json configs[1])"))
+                + (f" [DEBUG depth {args.layers}: not the headline config]" if args.layers else
+                   " (BASELINE.json configs[1])" if (args.model, B, S, new, args.gpu_percentage) == ("opt-30b", 64, 256, 32, 100) else
+                   " (BASELINE.json configs[3])" if (args.model, B, S, new) == ("opt-66b", 64, 512, 64) else ""))
     config = {"workload": workload, "parallelism": f"tp{world}", "l2": "inputs_exceed_l2 (weights+KV per step >> 126 MB)",
               "cuda_graphs": not args.no_graphs}
 

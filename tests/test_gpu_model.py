@@ -262,6 +262,31 @@ def test_kv_spill_does_not_change_results(lia):
         torch.cuda.empty_cache()
 
 
+def test_host_layer_pool_streams_full_byte_count(lia, monkeypatch):
+    """LIA_HOST_LAYER_POOL (host RAM smaller than the streamed weights, OPT-175B): streamed layers alias `pool`
+    distinct pinned slabs; the bytes crossing PCIe per forward are those of the full model and the result is that
+    of the model whose streamed layer j holds the weights of streamed layer j % pool."""
+    cfg = lia.modeling_opt.get_config("opt-1.3b")
+    cfg.num_hidden_layers = 5
+    ids = torch.randint(3, cfg.vocab_size, (4, 48), generator=torch.Generator().manual_seed(3))
+    monkeypatch.setenv("LIA_HOST_LAYER_POOL", "2")
+    m = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=9, gpu_percentage=20)          # 1 resident, 4 streamed
+    dec = m.model.decoder
+    assert dec.host_pool == 2 and len(dec.host_slabs) == 4 and dec.host_arena.nbytes == 2 * m.layout.nbytes
+    assert [t.data_ptr() for t in dec.host_slabs[2:]] == [t.data_ptr() for t in dec.host_slabs[:2]]
+    tok = m.generate(ids, max_new_tokens=4, min_new_tokens=4, gpu_percentage=20)
+    assert dec.streamer.stats()["bytes"] >= 4 * 4 * m.layout.nbytes                       # 4 forwards x 4 streamed layers
+    monkeypatch.delenv("LIA_HOST_LAYER_POOL")
+    from lia_b200.weights import random_layer
+    ref = lia.OPTForCausalLM(cfg, "cuda")
+    ref.model.decoder.load_embeddings({"embed_tokens": dec.embed_tokens, "embed_positions": dec.embed_positions,
+                                       "final_ln_w": dec.final_ln_w, "final_ln_b": dec.final_ln_b})
+    src = [0, 1, 2, 1, 2]                                                                  # layer i holds generator layer src[i]
+    ref.model.decoder.load_layers(lambda i, dev: random_layer(cfg.hidden_size, cfg.ffn_dim, 9 * 100003 + 1000 + src[i], dev,
+                                                              "normal", cfg.init_std), 100)
+    assert torch.equal(ref.generate(ids, max_new_tokens=4, min_new_tokens=4), tok)
+
+
 def test_full_size_layer_properties(lia):
     """OPT-30B layer dims at the bench batch (B=64): decode output vs oracle, KV round trip, and
     batch-permutation equivariance (a size-independent property of the path)."""
