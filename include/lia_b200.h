@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LIA_ABI_VERSION 2
+#define LIA_ABI_VERSION 3
 
 typedef void* lia_stream_t; /* cudaStream_t */
 
@@ -119,6 +119,15 @@ int lia_kv_append_bf16(const void* q, const void* k, const void* v, void* q_out,
  * an all-ones attention mask, M:368-378).  ids int64 [B,S]. */
 int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
                    int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream);
+
+/* The same with the positions OPTLearnedPositionalEmbedding.forward derives from an attention mask
+ * (M:368-378): p = cumsum(mask[b,:])[past_len+s] * mask[b,past_len+s] - 1, row = p + 2.  attention_mask
+ * is int64 [B, mask_ld] with mask_ld >= past_len + S (HF's mask covers past and current tokens,
+ * M:1127-1131); NULL means all ones.  Padded prompts change ONLY the positions on the reference's GPU
+ * branch: its attention rebuilds a pure causal mask in prefill and applies none in decode (A:446-449, A:500). */
+int lia_embed_masked_bf16(const int64_t* ids, const int64_t* attention_mask, int mask_ld, const void* embed_tokens,
+                          const void* embed_positions, void* out, int B, int S, int h, int past_len, int vocab,
+                          int max_pos_rows, lia_stream_t stream);
 
 /* next[b] = argmax_v logits[b, v] with logits[b, suppress_id] treated as -inf when
  * suppress_id >= 0 (min_new_tokens processor, lia/generation_utils.py:872-880; argmax at

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libliab200.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV = 0, 1, 2, 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 TP_MAX_WORLD = 8
 P2P_HANDLE_BYTES = 64
 
@@ -50,6 +50,8 @@ _PROTOTYPES = {
                                    c_int, c_int, c_float, c_void_p]),
     "lia_embed_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                c_void_p]),
+    "lia_embed_masked_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                      c_int, c_int, c_void_p]),
     "lia_argmax_bf16": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "lia_residual_add_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "lia_tp_ctl_bytes": (c_size_t, []),

@@ -4,19 +4,36 @@
 
 namespace {
 
-// hidden[b,s,:] = embed_tokens[ids[b,s]] + embed_positions[past_len + s + 2]
-// (lia/modeling_opt.py:1107-1142; positions from an all-ones mask, :368-378, offset 2 at :365)
+// hidden[b,s,:] = embed_tokens[ids[b,s]] + embed_positions[p + 2]  (lia/modeling_opt.py:1107-1142, offset 2 at :365)
+// where p is the learned-position index of OPTLearnedPositionalEmbedding.forward (lia/modeling_opt.py:368-378):
+//   p = cumsum(mask[b, :])[past_len + s] * mask[b, past_len + s] - 1
+// `mask` is the int64 attention mask [B, >= past_len + S] (row stride mask_ld); a null mask means all ones
+// (p = past_len + s), the only case the reference's benchmark produces.
 __global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ ids, const bf16* __restrict__ tok,
                                                     const bf16* __restrict__ pos, bf16* __restrict__ out, int S, int h,
-                                                    int past_len, int vocab, int max_pos_rows) {
+                                                    int past_len, int vocab, int max_pos_rows,
+                                                    const int64_t* __restrict__ mask, int mask_ld) {
   pdl_launch_dependents();
   pdl_wait();
   const int row = blockIdx.x;          // b*S + s
   const int s = row % S;
   long long id = ids[row];
   id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  int p = past_len + s + 2;
-  p = p >= max_pos_rows ? max_pos_rows - 1 : p;
+  long long p = past_len + s;
+  if (mask != nullptr) {
+    __shared__ long long part[4];
+    const int64_t* mr = mask + (size_t)(row / S) * mask_ld;
+    const int t = past_len + s;
+    long long c = 0;
+    for (int j = threadIdx.x; j <= t; j += 128) c += mr[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
+    __syncthreads();
+    p = (part[0] + part[1] + part[2] + part[3]) * mr[t] - 1;
+  }
+  p += 2;
+  p = p < 0 ? 0 : (p >= max_pos_rows ? max_pos_rows - 1 : p);
   const bf16* tr = tok + (size_t)id * h;
   const bf16* pr = pos + (size_t)p * h;
   bf16* o = out + (size_t)row * h;
@@ -144,17 +161,25 @@ extern "C" int lia_kv_append_bf16(const void* q, const void* k, const void* v, v
   return LIA_OK;
 }
 
-extern "C" int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
-                              int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream_) {
+extern "C" int lia_embed_masked_bf16(const int64_t* ids, const int64_t* attention_mask, int mask_ld, const void* embed_tokens,
+                                     const void* embed_positions, void* out, int B, int S, int h, int past_len, int vocab,
+                                     int max_pos_rows, lia_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   LIA_CHECK_ARG(ids && embed_tokens && embed_positions && out, "lia_embed_bf16: null pointer");
   LIA_CHECK_ARG(B > 0 && S > 0 && h > 0 && h % 8 == 0, "lia_embed_bf16: bad shape B=%d S=%d h=%d", B, S, h);
   LIA_CHECK_ARG(past_len >= 0 && past_len + S + 2 <= max_pos_rows, "lia_embed_bf16: positions %d..%d exceed the table (%d rows)", past_len + 2, past_len + S + 1, max_pos_rows);
+  LIA_CHECK_ARG(attention_mask == nullptr || mask_ld >= past_len + S, "lia_embed_masked_bf16: mask rows hold %d columns, need %d", mask_ld, past_len + S);
   lia_launch(embed_kernel, dim3(B * S), dim3(128), 0, stream, ids, reinterpret_cast<const bf16*>(embed_tokens),
                                            reinterpret_cast<const bf16*>(embed_positions), reinterpret_cast<bf16*>(out), S, h,
-                                           past_len, vocab, max_pos_rows);
+                                           past_len, vocab, max_pos_rows, attention_mask, mask_ld);
   LIA_LAUNCH_CHECK();
   return LIA_OK;
+}
+
+extern "C" int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
+                              int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream_) {
+  return lia_embed_masked_bf16(ids, nullptr, 0, embed_tokens, embed_positions, out, B, S, h, past_len, vocab, max_pos_rows,
+                               stream_);
 }
 
 extern "C" int lia_argmax_bf16(const void* logits, int64_t* next, int B, int V, int suppress_id, lia_stream_t stream_) {

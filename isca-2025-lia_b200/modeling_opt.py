@@ -131,6 +131,8 @@ class _GenState:
         self.Tmax = S + new
         self.beam_idx = torch.zeros(self.Tmax, B, dtype=torch.long, device=dev)
         self.prompt = torch.zeros(B, S, dtype=torch.int64, device=dev)
+        # attention mask of prompt + generated tokens; generated columns stay 1 (greedy_search.py:411 appends ones)
+        self.mask = torch.ones(B, self.Tmax, dtype=torch.int64, device=dev)
         self.steps_tok = torch.zeros(max(new, 1), B, dtype=torch.int64, device=dev)
         mb = max(1, B // max(1, num_minibatch))
         rows = max(mb * S, B)
@@ -447,7 +449,11 @@ class OPTDecoder:
             beam = past_key_values[0][3]
         mb = B if S == 1 else max(1, B // max(1, num_minibatch or 1))
         ws = self.workspace(max(mb * S, B), B)
-        x = ops.embed(ids, self.embed_tokens, self.embed_positions, past_len).view(B * S, cfg.hidden_size)   # M:1107-1142
+        am = None
+        if attention_mask is not None:                 # only the learned positions depend on it (M:368-378; A:446-449, A:500)
+            am = attention_mask.to(self.device, torch.int64).contiguous()
+        x = ops.embed(ids, self.embed_tokens, self.embed_positions, past_len,
+                      attention_mask=am).view(B * S, cfg.hidden_size)                                          # M:1107-1142
         self.run_layers(x, kcs, vcs, B, S, past_len, num_minibatch, ws)
         hidden = ops.layernorm(x, self.final_ln_w, self.final_ln_b, LN_EPS).view(B, S, cfg.hidden_size)       # M:1563-1564
         T = past_len + S
@@ -573,7 +579,8 @@ class OPTForCausalLM:
     def _prefill(self, st, num_minibatch, suppress):
         dec, cfg = self.model.decoder, self.config
         B, S = st.B, st.S
-        ops.embed(st.prompt, dec.embed_tokens, dec.embed_positions, 0, out=st.x.view(B, S, cfg.hidden_size))
+        ops.embed(st.prompt, dec.embed_tokens, dec.embed_positions, 0, out=st.x.view(B, S, cfg.hidden_size),
+                  attention_mask=st.mask)
         dec.run_layers(st.x, st.kc, st.vc, B, S, 0, num_minibatch, st.ws, st.spill)
         st.xd.copy_(st.x.view(B, S, cfg.hidden_size)[:, -1, :])                           # models.py:430 last token only
         self._head_and_pick(st, st.xd, 0, suppress)
@@ -583,7 +590,7 @@ class OPTForCausalLM:
         dec, cfg = self.model.decoder, self.config
         past = st.S + t - 1
         ops.embed(st.steps_tok[t - 1].view(st.B, 1), dec.embed_tokens, dec.embed_positions, past,
-                  out=st.xd.view(st.B, 1, cfg.hidden_size))
+                  out=st.xd.view(st.B, 1, cfg.hidden_size), attention_mask=st.mask)
         dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws, st.spill)
         self._head_and_pick(st, st.xd, t, suppress)
 
@@ -613,6 +620,16 @@ class OPTForCausalLM:
         graphs_ok = self.use_cuda_graphs and dec.streamer is None and st.spill is None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(new + 1)]
         st.prompt.copy_(input_ids, non_blocking=True)                                    # H2D (pinned host -> HBM)
+        pad = self.config.pad_token_id
+        if attention_mask is not None:
+            if tuple(attention_mask.shape) != (B, S):
+                raise ValueError(f"attention_mask must be [{B}, {S}], got {tuple(attention_mask.shape)}")
+            st.mask[:, :S].copy_(attention_mask, non_blocking=True)
+        elif pad is not None and pad != eos:
+            # generation_utils.py:469-485: without a mask, pad ids in the prompt define one (all ones when there are none)
+            st.mask[:, :S].copy_(st.prompt.ne(pad))
+        else:
+            st.mask[:, :S].fill_(1)
         ev[0].record()
         self._prefill(st, num_minibatch, eos if 0 < min_new else -1)
         ev[1].record()

@@ -155,15 +155,27 @@ def attn_decode_workspace(B, H, d, device, max_splits=32):
     return torch.empty(n // 4, dtype=torch.float32, device=device)
 
 
-def embed(ids, embed_tokens, embed_positions, past_len, out=None):
-    """Token + learned positional embedding (lia/modeling_opt.py:1107-1142, 368-378)."""
+def embed(ids, embed_tokens, embed_positions, past_len, out=None, attention_mask=None):
+    """Token + learned positional embedding (lia/modeling_opt.py:1107-1142, 368-378).  ``attention_mask``
+    (int64 [B, >= past_len + S], may be a column-slice view of a wider buffer) selects the positions the
+    reference derives from its cumsum; None means all ones."""
     _req(ids, "ids", torch.int64); _req(embed_tokens, "embed_tokens"); _req(embed_positions, "embed_positions")
     B, S = ids.shape
     V, h = embed_tokens.shape
     if out is None:
         out = torch.empty(B, S, h, dtype=BF16, device=ids.device)
-    check(_lib.load().lia_embed_bf16(_p(ids), _p(embed_tokens), _p(embed_positions), _p(_req(out, "out")), B, S, h,
-                                     past_len, V, embed_positions.shape[0], _stream()), "lia_embed_bf16")
+    mask_ptr, mask_ld = None, 0
+    if attention_mask is not None:
+        am = attention_mask
+        if not (am.is_cuda and am.dtype == torch.int64 and am.dim() == 2 and am.shape[0] == B and am.stride(1) == 1):
+            raise _lib.LiaError(f"attention_mask: need a CUDA int64 [B, T] tensor with unit column stride, got {am.dtype} "
+                                f"{tuple(am.shape)} strides {am.stride()} on {am.device}")
+        if am.shape[1] < past_len + S:
+            raise _lib.LiaError(f"attention_mask has {am.shape[1]} columns, need past_len + S = {past_len + S}")
+        mask_ptr, mask_ld = am.data_ptr(), am.stride(0) if B > 1 else max(am.stride(0), am.shape[1])
+    check(_lib.load().lia_embed_masked_bf16(_p(ids), mask_ptr, mask_ld, _p(embed_tokens), _p(embed_positions),
+                                            _p(_req(out, "out")), B, S, h, past_len, V, embed_positions.shape[0], _stream()),
+          "lia_embed_masked_bf16")
     count_launches()
     return out
 

@@ -206,12 +206,72 @@ def gen_hf_model_case(name, V, h, H, L, P, B, S, new, seed):
     print("wrote", name, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def _lift_class_method(path, cls, method, ns):
+    """Compile one method of a top-level class of ``path`` as a plain function in ``ns``."""
+    src = open(path).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            for sub in node.body:
+                if isinstance(sub, ast.FunctionDef) and sub.name == method:
+                    text = ast.get_source_segment(src, sub)
+                    import textwrap
+                    exec(compile(textwrap.dedent(text), f"{path}:{cls}.{method}", "exec"), ns)
+                    return ns[method]
+    raise KeyError((cls, method))
+
+
+def gen_positions_case(name, seed):
+    """The reference's own OPTLearnedPositionalEmbedding.forward (lia/modeling_opt.py:368-378) and
+    _prepare_attention_mask_for_generation (lia/generation_utils.py:469-485), lifted at run time, on left-padded,
+    right-padded and hole-y masks.  forward() ends in ``super().forward(positions + self.offset)``: it is executed
+    with ``super`` bound to a shim whose forward is nn.Embedding's lookup, so the stored rows are the reference's."""
+    M_PATH = os.path.join(REF, "lia/modeling_opt.py")
+    GU_PATH = os.path.join(REF, "lia/generation_utils.py")
+    g = torch.Generator().manual_seed(seed)
+    P, h, B, S, new = 40, 16, 6, 9, 4
+    table = torch.randn(P + 2, h, generator=g).to(torch.bfloat16)
+
+    class _Super:
+        def forward(self_inner, idx):
+            _Super.last = idx.clone()
+            return F.embedding(idx, table)
+
+    class _Self:
+        offset = 2                                                           # lia/modeling_opt.py:365
+    ns = {"torch": torch, "nn": nn, "F": F, "Optional": Optional, "Tuple": Tuple, "Union": Union, "List": List,
+          "super": lambda *a: _Super()}
+    fwd = _lift_class_method(M_PATH, "OPTLearnedPositionalEmbedding", "forward", ns)
+    prep = _lift_class_method(GU_PATH, "GenerationMixin", "_prepare_attention_mask_for_generation", dict(ns))
+    ids = torch.randint(3, 300, (B, S), generator=g)
+    ids[0, :3] = 1                      # left padding
+    ids[1, :1] = 1
+    ids[2, -2:] = 1                     # right padding
+    ids[3, 4] = 1                       # a hole
+    ids[4, :] = 1                       # fully padded row
+    mask = prep(None, ids, 1, 2)
+    assert mask.sum() < mask.numel()
+    mask_nopad = prep(None, ids.clamp(min=3), 1, 2)
+    mask_pad_is_eos = prep(None, ids, 1, 1)
+    out = {"P": P, "h": h, "B": B, "S": S, "new": new, "table": bf16_bits(table), "ids": ids.numpy(),
+           "mask": mask.numpy(), "mask_nopad": mask_nopad.numpy(), "mask_pad_is_eos": mask_pad_is_eos.numpy()}
+    full = mask
+    for step in range(new + 1):
+        past = 0 if step == 0 else S + step - 1
+        rows = fwd(_Self(), full, past)
+        out[f"pos{step}"] = _Super.last.numpy()
+        out[f"rows{step}"] = bf16_bits(rows)
+        full = torch.cat([full, full.new_ones(B, 1)], dim=-1)                 # greedy_search.py:411
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print("wrote", name, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)                                   # bit-stable CPU reductions
     gen_layer_case("layer_d64", B=3, S=8, h=128, H=2, new=3, seed=11)
     gen_layer_case("layer_d128", B=2, S=5, h=128, H=1, new=2, seed=12)
     gen_layer_case("layer_ragged", B=1, S=1 + 16, h=192, H=3, new=1, seed=13)   # h not a power of two
+    gen_positions_case("positions_padded", seed=31)
     gen_hf_model_case("model_hf_tiny", V=320, h=64, H=1, L=2, P=48, B=3, S=7, new=5, seed=21)
 
 

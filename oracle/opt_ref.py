@@ -19,7 +19,10 @@ Parity pin: ``tests/test_oracle_golden.py`` checks ``layer_forward`` BIT-EXACTLY
 against outputs of the reference's own ``OPTDecoderLayer_forward`` /
 ``_OPTAttention_forward`` executed in the build container
 (``oracle/gen_golden.py`` -> ``tests/golden/layer_*.npz``) and the whole-model
-functions against stock ``transformers.OPTForCausalLM`` (``model_hf_tiny.npz``).
+functions against stock ``transformers.OPTForCausalLM`` (``model_hf_tiny.npz``);
+``positions_from_mask`` / ``prepare_attention_mask`` against the reference's own
+``OPTLearnedPositionalEmbedding.forward`` and ``_prepare_attention_mask_for_generation``
+run on padded prompts (``positions_padded.npz``).
 The reference holds no golden vectors of its own for this path.
 
 Weight dictionaries use the keys
@@ -152,14 +155,25 @@ def lm_logits(model, hidden):
     return torch.matmul(hidden[:, -1:, :], model["embed_tokens"].t()).contiguous()
 
 
-def greedy_generate(model, input_ids, max_new_tokens, eos_token_id=2, collect_logits=None):
+def prepare_attention_mask(input_ids, pad_token_id=1, eos_token_id=2):
+    """GU:469-485 (_prepare_attention_mask_for_generation): when the caller passes no mask, pad ids in
+    the prompt define it, provided pad != eos; otherwise all ones."""
+    if pad_token_id is not None and bool((input_ids == pad_token_id).any()) and pad_token_id != eos_token_id:
+        return input_ids.ne(pad_token_id).long()
+    return torch.ones(input_ids.shape[:2], dtype=torch.long, device=input_ids.device)
+
+
+def greedy_generate(model, input_ids, max_new_tokens, eos_token_id=2, collect_logits=None, attention_mask=None,
+                    pad_token_id=1):
     """GS:144-429 with the benchmark's kwargs (RG:179-182): greedy, min_new_tokens ==
     max_new_tokens so eos is suppressed on every step (GU:872-880), stop on length
-    only (GS:425).  Returns ids [B, S+new]."""
+    only (GS:425).  Returns ids [B, S+new].  The mask (given, or derived as GU:469-485 does) only
+    moves the learned positions (M:368-378): the GPU branch's attention ignores padding (A:446-449, A:500)."""
     B, S = input_ids.shape
     cache = new_cache(model, B, S + max_new_tokens)
     ids = input_ids
-    mask = torch.ones(B, S, dtype=torch.long, device=input_ids.device)
+    mask = (attention_mask.long() if attention_mask is not None
+            else prepare_attention_mask(input_ids, pad_token_id, eos_token_id))
     past = 0
     cur = input_ids
     for _ in range(max_new_tokens):

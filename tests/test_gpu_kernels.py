@@ -186,6 +186,32 @@ def test_embed_argmax_residual(ops):
     assert torch.equal(ops.residual_add(a, b).float(), r16(b.float() + a.float()))
 
 
+def test_embed_positions_from_padded_mask_vs_reference_golden(ops, golden_dir):
+    """lia_embed_masked_bf16 against rows produced by the reference's own OPTLearnedPositionalEmbedding.forward
+    (tests/golden/positions_padded.npz): left/right padding, a hole, a fully padded row; prefill and decode steps."""
+    import os
+    import numpy as np
+    z = np.load(os.path.join(golden_dir, "positions_padded.npz"))
+    bits = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(BF16)   # noqa: E731
+    table = bits(z["table"]).cuda()
+    B, S, new, h = int(z["B"]), int(z["S"]), int(z["new"]), int(z["h"])
+    tok = torch.zeros(8, h, dtype=BF16, device="cuda")                      # token rows are zero: out == position row
+    buf = torch.ones(B, S + new + 3, dtype=torch.int64, device="cuda")      # wider than needed: row stride != columns
+    buf[:, :S] = torch.from_numpy(z["mask"]).cuda()
+    for step in range(new + 1):
+        past, s = (0, S) if step == 0 else (S + step - 1, 1)
+        ids = torch.zeros(B, s, dtype=torch.int64, device="cuda")
+        out = ops.embed(ids, tok, table, past, attention_mask=buf[:, :past + s])
+        assert torch.equal(out.view(torch.int16).cpu(), bits(z[f"rows{step}"]).view(torch.int16)), step
+    # no mask == all-ones mask
+    ids = torch.randint(0, 8, (B, S), device="cuda")
+    tok = rnd(8, h, seed=9)
+    assert torch.equal(ops.embed(ids, tok, table, 3), ops.embed(ids, tok, table, 3, attention_mask=torch.ones(B, S + 3, dtype=torch.int64, device="cuda")))
+    from lia_b200._lib import LiaError
+    with pytest.raises(LiaError):
+        ops.embed(ids, tok, table, 3, attention_mask=torch.ones(B, S, dtype=torch.int64, device="cuda"))   # too few columns
+
+
 def test_errors_are_loud(ops):
     from lia_b200._lib import LiaError
     a = rnd(4, 12)          # K not a multiple of 8

@@ -203,6 +203,60 @@ def test_greedy_tokens_and_hidden_vs_oracle(lia, cfgname, L, B, S, new, nmb):
     print(f"{cfgname}: {n_ident}/{B} sequences identical for all {new} tokens; the rest diverge at a bf16 near-tie")
 
 
+def test_padded_prompts_follow_the_reference_mask_semantics(lia):
+    """Ragged (padded) prompts.  On the reference's GPU branch the attention mask moves only the learned positions
+    (cumsum rule, lia/modeling_opt.py:368-378): attention is pure-causal in prefill and unmasked in decode
+    (attentions.py:446-449, 500), and generate() derives the mask from pad ids when none is passed
+    (lia/generation_utils.py:469-485).  Hidden states vs the oracle fed the same mask; generate() with the implicit
+    and the explicit mask must agree bit for bit and react to the mask."""
+    from oracle import opt_ref
+    cfg = lia.OPTConfig(hidden_size=256, num_hidden_layers=2, num_attention_heads=2, ffn_dim=1024, vocab_size=512,
+                        max_position_embeddings=64)
+    m = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=4, bias_std=0.02, ln_std=0.05)
+    om = _oracle_model(m, "cuda")
+    B, S, new = 5, 12, 4
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(5))
+    ids[0, :4] = cfg.pad_token_id          # left padding
+    ids[1, :1] = cfg.pad_token_id
+    ids[2, -3:] = cfg.pad_token_id         # right padding
+    ids[3, 6] = cfg.pad_token_id           # a hole
+    mask = ids.ne(cfg.pad_token_id).long()
+    dec = m.model.decoder
+    hidden, past = dec(input_ids=ids.cuda(), attention_mask=mask.cuda(), max_new_tokens=new)
+    nxt = torch.randint(3, cfg.vocab_size, (B, 1), generator=torch.Generator().manual_seed(6))
+    mask1 = torch.cat([mask, mask.new_ones(B, 1)], 1)
+    hidden1, _ = dec(input_ids=nxt.cuda(), attention_mask=mask1.cuda(), past_key_values=past, max_new_tokens=new)
+    with torch.no_grad():
+        cache = opt_ref.new_cache(om, B, S + new)
+        href = opt_ref.decoder_forward(om, ids.cuda(), mask.cuda(), cache, 0)
+        href1 = opt_ref.decoder_forward(om, nxt.cuda(), mask1.cuda(), cache, S)
+        hones = opt_ref.decoder_forward(om, ids.cuda(), torch.ones_like(mask).cuda(), opt_ref.new_cache(om, B, S + new), 0)
+    assert rel_err(hidden, href) <= 3 * REL_TOL and rel_err(hidden1, href1) <= 3 * REL_TOL      # chained through 2 layers
+    assert rel_err(hidden, hones) > 10 * REL_TOL                      # the mask matters: all-ones positions are far off
+    with pytest.raises(ValueError):
+        dec(input_ids=ids.cuda(), attention_mask=mask1.cuda(), max_new_tokens=new)               # M:1127-1131
+    kw = dict(max_new_tokens=new, min_new_tokens=new, prefill_policy=0, decoding_policy=0)
+    outs = [m.generate(ids, **kw) for _ in range(3)]                  # implicit mask; eager, capture, replay
+    outs += [m.generate(ids, attention_mask=mask, **kw)]
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    with torch.no_grad():
+        ref_logits = []
+        ref = opt_ref.greedy_generate(om, ids.cuda(), new, collect_logits=ref_logits).cpu()
+    for b in range(B):
+        diff = torch.nonzero(outs[0][b] != ref[b]).flatten()
+        if diff.numel():                                              # only a bf16 near-tie may flip a token
+            t = int(diff[0]) - S
+            lg = ref_logits[t][b].float().cpu()
+            lg[cfg.eos_token_id] = float("-inf")
+            margin = (lg[ref[b, S + t]] - lg[outs[0][b, S + t]]).item()
+            assert 0 <= margin <= 3 * _ulp(lg[ref[b, S + t]]).item(), (b, t, margin)
+    # after an unpadded call on the same shape the mask state must not leak
+    clean = ids.clamp(min=3)
+    a = m.generate(clean, **kw)
+    assert torch.equal(a, m.generate(clean, attention_mask=torch.ones_like(mask), **kw))
+
+
 def test_scheduling_knobs_do_not_change_results(lia):
     """gpu_percentage (streaming) and num_minibatch are scheduling knobs: outputs must be bit-identical
     (the reference's minibatch quirk, SURVEY.md A.4, is not reproduced)."""

@@ -77,3 +77,24 @@ def test_tp_sharding_restatement_sums_to_full(golden_dir):
         s = opt_ref.shard_layer(wf, meta["H"], r, 2)
         parts = parts + torch.relu(x @ s["fc1_w"].t() + s["fc1_b"]) @ s["fc2_w"].t()
     torch.testing.assert_close(parts, full, atol=1e-4, rtol=1e-4)
+
+
+def test_positions_and_mask_rule_bit_exact_vs_reference(golden_dir):
+    """Padded prompts (left, right, a hole, a fully padded row): the learned-position indices and embedding rows
+    of the reference's own OPTLearnedPositionalEmbedding.forward, and its mask-from-pad-ids rule."""
+    z = np.load(os.path.join(golden_dir, "positions_padded.npz"))
+    ids, table = torch.from_numpy(z["ids"]), _bf16(z["table"])
+    mask = opt_ref.prepare_attention_mask(ids, 1, 2)
+    assert np.array_equal(mask.numpy(), z["mask"])
+    assert np.array_equal(opt_ref.prepare_attention_mask(ids.clamp(min=3), 1, 2).numpy(), z["mask_nopad"])
+    assert np.array_equal(opt_ref.prepare_attention_mask(ids, 1, 1).numpy(), z["mask_pad_is_eos"])
+    B, S, new = int(z["B"]), int(z["S"]), int(z["new"])
+    model = {"embed_tokens": torch.zeros(4, table.shape[1], dtype=torch.bfloat16), "embed_positions": table}
+    full = mask
+    for step in range(new + 1):
+        past = 0 if step == 0 else S + step - 1
+        pos = opt_ref.positions_from_mask(full, past)
+        assert np.array_equal(pos.numpy(), z[f"pos{step}"]), step
+        rows = opt_ref.embed(model, torch.zeros(B, pos.shape[1], dtype=torch.long), full, past)   # token rows are zero
+        assert torch.equal(rows.view(torch.int16), _bf16(z[f"rows{step}"]).view(torch.int16))
+        full = torch.cat([full, full.new_ones(B, 1)], dim=-1)
