@@ -110,6 +110,48 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA-pair (cta_group::2) variants: the two CTAs of a cluster drive ONE 256-row MMA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of the same shared-memory location in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to a barrier that may live in the peer CTA of the pair
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t cluster_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_f16_pair(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint32_t bar) {
@@ -212,10 +254,12 @@ __device__ __forceinline__ void epilogue_store8(const EpiParams& p, int m, int n
   epilogue_finish8(p, m, n, v, b, res);
 }
 
-template <bool SWAP, int BN, int STAGES>
+// PAIR: two CTAs (one cluster, one TPC) compute a 256 x BN tile with tcgen05.mma.cta_group::2; each CTA stages its own
+// 128 rows of A and only HALF of the B tile, so a stage is 32 KB instead of 48 KB and six stages fit.
+template <bool SWAP, int BN, int STAGES, bool PAIR = false>
 struct SmemLayout {
   static constexpr int A_BYTES = TILE_A * BLOCK_K * 2;
-  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int B_BYTES = (PAIR ? BN / 2 : BN) * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_BYTES = SWAP ? BN * SWAP_LD * 4 : 4 * 32 * 128;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES + STAGING_BYTES;
@@ -243,7 +287,10 @@ struct Sched {
   // divisions are software routines of ~100 instructions each and this code is inlined into three roles)
   int k_blocks, tiles_a, tiles_b;
   unsigned pos, end;   // SWAP: flat k-block position; NORMAL: unit index / count
-  __device__ Sched(int k_blocks_, int tiles_a_, int tiles_b_, int streamk) : k_blocks(k_blocks_), tiles_a(tiles_a_), tiles_b(tiles_b_) {
+  unsigned step;       // NORMAL: workers (CTAs, or CTA pairs) sharing the unit list
+  int group_m;         // NORMAL: A tiles per raster group
+  __device__ Sched(int k_blocks_, int tiles_a_, int tiles_b_, int streamk, bool pair = false)
+      : k_blocks(k_blocks_), tiles_a(tiles_a_), tiles_b(tiles_b_), step(pair ? gridDim.x >> 1 : gridDim.x), group_m(pair ? GROUP_M / 2 : GROUP_M) {
     if (SWAP) {
       if (streamk) {
         const unsigned total = (unsigned)tiles_a * (unsigned)k_blocks;
@@ -254,7 +301,7 @@ struct Sched {
         end = ((unsigned)tiles_a * (blockIdx.x + 1) / gridDim.x) * (unsigned)k_blocks;
       }
     } else {
-      pos = blockIdx.x;
+      pos = pair ? blockIdx.x >> 1 : blockIdx.x;
       end = (unsigned)tiles_a * (unsigned)tiles_b;
     }
   }
@@ -269,16 +316,16 @@ struct Sched {
       pos += (unsigned)(w.kb1 - w.kb0);
     } else {
       const int u = (int)pos;
-      const int group_size = GROUP_M * tiles_b;
+      const int group_size = group_m * tiles_b;
       const int group = u / group_size;
-      const int first = group * GROUP_M;
-      const int gm = min(GROUP_M, tiles_a - first);
+      const int first = group * group_m;
+      const int gm = min(group_m, tiles_a - first);
       const int r = u - group * group_size;
       w.ta = first + r % gm;
       w.tb = r / gm;
       w.kb0 = 0;
       w.kb1 = k_blocks;
-      pos += gridDim.x;
+      pos += step;
     }
     return true;
   }
@@ -452,13 +499,16 @@ __device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
 }
 
 // ------------------------------------------------------------------ the kernel
-template <bool SWAP, int BN, int STAGES, bool TP>
+template <bool SWAP, int BN, int STAGES, bool TP, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                         const __grid_constant__ EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
                         int* __restrict__ flags, unsigned long long* __restrict__ trace) {
-  using L = SmemLayout<SWAP, BN, STAGES>;
+  static_assert(!PAIR || (!SWAP && !TP && BN == 256), "CTA pairs: plain prefill projections with 256-wide tiles only");
+  using L = SmemLayout<SWAP, BN, STAGES, PAIR>;
+  // PAIR: rank in the 2-CTA cluster; rank 0 (the "leader") issues every MMA and owns the full / tempty barriers
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -479,23 +529,31 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(full_bar(s), 1);      // PAIR: only the leader's is used; it collects the bytes of both CTAs' loads
+      mbar_init(empty_bar(s), 1);     // PAIR: the leader's commit arrives on both CTAs' copies
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
-      mbar_init(tempty_bar(a), 4);
+      mbar_init(tempty_bar(a), PAIR ? 8 : 4);   // PAIR: the epilogue warps of both CTAs release the leader's accumulator
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
-                 "r"((uint32_t)tmem_cols(BN))
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {   // collective over the pair: one warp of EACH CTA issues it
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"((uint32_t)tmem_cols(BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32((const void*)tmem_ptr_smem)),
+                   "r"((uint32_t)tmem_cols(BN))
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   if (threadIdx.x == 0) stamp(trace, 1);
@@ -523,14 +581,22 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         }
       }
       pdl_wait();
-      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk, PAIR);
       Work w;
       int idx = 0;
       while (sched.next(w)) {
         for (int kb = w.kb0; kb < w.kb1; ++kb, ++idx) {
           const uint32_t sa = smem_base + stage * L::STAGE_BYTES;
           const uint32_t sb = sa + L::A_BYTES;
-          if (idx < npre) {
+          if (PAIR) {
+            // this CTA's 128 rows of the 256-row A tile and its half of the B tile; every byte is credited to the
+            // LEADER's full barrier, which expects both CTAs' stages (the leader alone arrives on it)
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            const uint32_t fb = mapa_u32(full_bar(stage), 0);
+            if (cta_rank == 0) mbar_expect_tx(full_bar(stage), 2 * L::STAGE_BYTES);
+            tma_load_2d_pair(sa, &tmA, kb * BLOCK_K, (w.ta * 2 + (int)cta_rank) * TILE_A, fb);
+            tma_load_2d_pair(sb, &tmB, kb * BLOCK_K, w.tb * BN + (int)cta_rank * (BN / 2), fb);
+          } else if (idx < npre) {
             tma_load_2d(sb, &tmB, kb * BLOCK_K, w.tb * BN, full_bar(stage));   // A tile already in flight
           } else {
             mbar_wait(empty_bar(stage), phase ^ 1u);
@@ -551,14 +617,14 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(TILE_A, BN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc(PAIR ? 2 * TILE_A : TILE_A, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       bool first_full = true;
-      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+      Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk, PAIR);
       Work w;
       while (sched.next(w)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
@@ -577,15 +643,18 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in the >>4 address field
-            tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            if (PAIR) tcgen05_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
+            else tcgen05_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb > w.kb0 || k > 0) ? 1u : 0u);
           }
-          tcgen05_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
+          if (PAIR) tcgen05_commit_pair(empty_bar(stage));   // frees the stage in BOTH CTAs
+          else tcgen05_commit(empty_bar(stage));   // frees the smem stage when these MMAs have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        tcgen05_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        if (PAIR) tcgen05_commit_pair(tfull_bar(acc));   // each CTA's epilogue drains its own 128 rows
+        else tcgen05_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         stamp(trace, 4);
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
@@ -685,7 +754,8 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       sig_done_u = u;                         // done_flag[u] is raised by the next tp_flush_signals()
     };
-    Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk);
+    Sched<SWAP> sched(k_blocks, tiles_a, tiles_b, streamk, PAIR);
+    const int row_tile = PAIR ? 2 : 1;        // 128-row blocks per A tile; this CTA drains block `cta_rank`
     Work w;
     while (sched.next(w)) {
       // SWAP: this thread finishes columns [n_col, n_col+8) of rows m0, m0+8, ... -- fetch what the
@@ -737,7 +807,10 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             // all TMEM reads of this accumulator are done: hand it back to the MMA warp early
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (lane == 0) {
+              if (PAIR && cta_rank != 0) mbar_arrive_cluster(mapa_u32(tempty_bar(acc), 0));
+              else mbar_arrive(tempty_bar(acc));
+            }
           } else {
             __syncwarp();
           }
@@ -748,7 +821,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             uint4 q;
             const uint32_t addr = stg + r * 128 + ((ch ^ (r & 7)) << 4);
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
-            const int m = w.ta * TILE_A + ew * 32 + r;
+            const int m = (w.ta * row_tile + (int)cta_rank) * TILE_A + ew * 32 + r;
             const int n = w.tb * BN + c0 + ch * 8;
             if (m < p.M && n < p.N) {
               float f[8];
@@ -1036,10 +1109,12 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   tcgen05_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();   // no CTA leaves (or frees TMEM) while its peer may still arrive on its barriers
   if (threadIdx.x == 0) stamp(trace, 7);
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)tmem_cols(BN)) : "memory");
   }
 }
 
@@ -1084,6 +1159,7 @@ int make_tmap(CUtensorMap* map, const void* base, int rows, int K, int box_rows)
 
 struct Plan {
   bool swap;
+  bool pair;     // NORMAL: 2-CTA clusters, tcgen05.mma.cta_group::2 on 256 x 256 tiles
   int bn;
   int grid;      // CTAs
   int streamk;   // SWAP: split tiles across CTAs at k-block granularity
@@ -1102,8 +1178,15 @@ int gemm_cta_budget() {
   return sms;
 }
 
-Plan make_plan(int M, int N, int K) {
+// LIA_GEMM_2CTA=1 selects the CTA-pair prefill kernel (off by default until it has been measured on a B200)
+bool pair_enabled() {
+  const char* env = getenv("LIA_GEMM_2CTA");
+  return env && atoi(env) != 0;
+}
+
+Plan make_plan(int M, int N, int K, bool allow_pair = false) {
   Plan pl;
+  pl.pair = false;
   const int sms = gemm_cta_budget();
   pl.k_blocks = (K + BLOCK_K - 1) / BLOCK_K;
   pl.swap = (M <= 128);
@@ -1124,10 +1207,12 @@ Plan make_plan(int M, int N, int K) {
     if (!pl.streamk && pl.grid > pl.tiles_a) pl.grid = pl.tiles_a;
   } else {
     pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
-    pl.tiles_a = (M + TILE_A - 1) / TILE_A;
+    pl.pair = allow_pair && pl.bn == 256 && M >= 4 * TILE_A && sms >= 2 && pair_enabled();
+    pl.tiles_a = pl.pair ? (M + 2 * TILE_A - 1) / (2 * TILE_A) : (M + TILE_A - 1) / TILE_A;
     pl.tiles_b = (N + pl.bn - 1) / pl.bn;
     const int units = pl.tiles_a * pl.tiles_b;
-    pl.grid = units < sms ? units : sms;
+    if (pl.pair) pl.grid = 2 * (units < sms / 2 ? units : sms / 2);
+    else pl.grid = units < sms ? units : sms;
   }
   return pl;
 }
@@ -1159,6 +1244,50 @@ unsigned long long* trace_buffer() {
     }
   }
   return buf;
+}
+
+// CTA-pair launch: clusters of two CTAs (one TPC) + programmatic dependent launch
+int launch_pair(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, cudaStream_t stream) {
+  constexpr int BN = 256, STAGES = 6;
+  using L = SmemLayout<false, BN, STAGES, true>;
+  static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
+  auto kern = lia_gemm_tcgen05_kernel<false, BN, STAGES, false, true>;
+  static bool configured = false;
+  if (!configured) {
+    LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(pl.grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = L::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // persistent schedule: never launch more clusters than can be co-resident (a TPC with one SM fused off holds none)
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = lia_sm_count() / 2;
+    }
+    max_clusters = n;
+  }
+  if (pl.grid > 2 * max_clusters) cfg.gridDim = dim3(2 * max_clusters);
+  cfg.numAttrs = lia_pdl_enabled() ? 2 : 1;
+  float* ws = nullptr;
+  int* flags = nullptr;
+  unsigned long long* tr = nullptr;
+  LIA_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ep, pl.k_blocks, pl.streamk, pl.tiles_a, pl.tiles_b, ws, flags, tr));
+  return LIA_OK;
 }
 
 template <bool SWAP, int BN, int STAGES, bool TP>
@@ -1244,7 +1373,7 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
     if (epilogue == LIA_EPI_BIAS_RESIDUAL || epilogue == EPI_TP)
       LIA_CHECK_ARG(residual != nullptr, "%s: residual epilogue needs residual", fn);
   }
-  Plan pl = make_plan(M, N, K);
+  Plan pl = make_plan(M, N, K, /*allow_pair=*/tp == nullptr);
   LIA_CHECK_ARG((long long)pl.tiles_a * pl.k_blocks * (pl.grid + 1) < (1ll << 31) && (long long)pl.tiles_a * pl.tiles_b < (1ll << 31),
                 "%s: problem too large for the 32-bit tile scheduler (M=%d N=%d K=%d)", fn, M, N, K);
   if (tp != nullptr) {
@@ -1302,7 +1431,8 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
     }
   } else {
     if ((rc = make_tmap(&tmA, A, M, K, TILE_A)) != LIA_OK) return rc;
-    if ((rc = make_tmap(&tmB, W, N, K, pl.bn)) != LIA_OK) return rc;
+    if ((rc = make_tmap(&tmB, W, N, K, pl.pair ? pl.bn / 2 : pl.bn)) != LIA_OK) return rc;
+    if (pl.pair) return launch_pair(pl, tmA, tmB, ep, stream);
     if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, flags, stream);
   }
