@@ -1,16 +1,12 @@
-"""Opt-in parity test of the CTA-pair (tcgen05.mma.cta_group::2) prefill GEMM, selected with LIA_GEMM_2CTA=1.
+"""Parity test of the CTA-pair (tcgen05.mma.cta_group::2) prefill GEMM -- the default for M >= 512 -- against the
+one-CTA 128 x 256 kernel (LIA_GEMM_2CTA=0).
 
-The kernel is off by default and this file is skipped unless LIA_TEST_2CTA=1, so an unmeasured kernel can never hang
-the regular `pytest -m gpu` run: `LIA_TEST_2CTA=1 timeout 180 python -m pytest tests/test_gpu_gemm_2cta.py -q -m gpu`.
 The pair kernel accumulates every output element over K in the same order as the one-CTA kernel (same 16-wide MMA
-steps, same sequence), so the two are expected to agree BIT FOR BIT; the fp32 reference bounds both."""
-import os
-
+steps, same sequence), so the two must agree BIT FOR BIT; the fp32 reference bounds both."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("LIA_TEST_2CTA", "0") == "0",
-                                                  reason="opt-in: set LIA_TEST_2CTA=1")]
+pytestmark = [pytest.mark.gpu]
 BF16 = torch.bfloat16
 
 
@@ -40,7 +36,7 @@ def test_pair_gemm_matches_one_cta_kernel(ops, monkeypatch, M, N, K, epilogue):
     w = rnd(N, K, std=K ** -0.5, seed=K + 1)
     bias = rnd(N, std=0.5, seed=5)
     res = rnd(M, N, seed=6) if epilogue == 2 else None
-    monkeypatch.delenv("LIA_GEMM_2CTA", raising=False)
+    monkeypatch.setenv("LIA_GEMM_2CTA", "0")
     y1 = ops.gemm(a, w, bias, epilogue=epilogue, residual=res)
     monkeypatch.setenv("LIA_GEMM_2CTA", "1")
     for rep in range(2):
