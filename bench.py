@@ -53,6 +53,36 @@ def peaks():
     return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
 
 
+def committed_traffic(pair):
+    """DRAM read+write bytes per launch of the prefill GEMM from the newest committed `ncu --set full` capture
+    (profiles/r*_traffic.json).  Prefers the capture of the kernel variant that is running (CTA pair or one-CTA);
+    says so when only the other variant has been captured."""
+    import glob
+    import re
+    want, other = ("pair", "one-cta") if pair else ("one-cta", "pair")
+    found = {}
+    for tj in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_traffic.json"))):
+        for name, rec in json.load(open(tj)).items():
+            m = re.search(r"lia_gemm_tcgen05_kernel<([^>]*)>", name)
+            if not m or "dram_bytes_per_launch_avg" not in rec:
+                continue
+            # template arguments <SWAP, BN, STAGES[, TP, PAIR]> as ncu prints them ("0, 256, 4" / "(bool)0, (int)256, ...")
+            a = [1 if x == "true" else 0 if x == "false" else int(x)
+                 for x in re.findall(r"\b(true|false|\d+)\b", re.sub(r"\([a-z ]+\)", "", m.group(1)))]
+            if len(a) < 3 or a[0] != 0 or a[1] != 256:
+                continue                                    # decode (swap-AB) or narrow-N variants
+            key = "pair" if (len(a) >= 5 and a[4] == 1) else "one-cta"
+            found[key] = (rec["dram_bytes_per_launch_avg"], os.path.basename(tj), name)
+    if want in found:
+        v, f, name = found[want]
+        return v, f"ncu --set full capture of {name} ({f})"
+    if other in found:
+        v, f, name = found[other]
+        return v, (f"from the ncu capture of {name} ({f}): the other prefill variant "
+                   f"({'one-CTA cta_group::1' if pair else 'CTA-pair cta_group::2'} kernel); the running variant has no committed capture yet")
+    return None, None
+
+
 class ClockSampler:
     """SM clock + throttle reasons during the timed region (NVML; nvidia-smi as a fallback)."""
 
@@ -251,16 +281,15 @@ def _main(args, json_out):
         flops = sum(2.0 * M_ * N_ * K_ for M_, N_, K_, _ in big)
         ms = sum(t for *_, t in big)
         ach = flops / (ms / 1e3) / 1e12
-        traffic = None
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
-        if os.path.exists(tj) and not args.layers and world == 1:
-            # DRAM read+write bytes per launch of this kernel from the committed `ncu --set full` capture
-            traffic = json.load(open(tj)).get("lia_gemm_tcgen05_kernel<0, 256, 4>", {}).get("dram_bytes_per_launch_avg")
+        traffic, traffic_note = None, None
+        if not args.layers and world == 1:
+            traffic, traffic_note = committed_traffic(os.environ.get("LIA_GEMM_2CTA", "1") != "0")
         roof = {"kernel": "lia_gemm_tcgen05_kernel (prefill projections)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic,
                 "launches": len(big), "avg_launch_ms": ms / len(big), "flops_per_launch": flops / len(big),
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step); burst "
-                + f"{pk['bf16_burst']}", "share_of_step": (ms / 1e3) / (sec / args.steps)}
+                + f"{pk['bf16_burst']}", "share_of_step": (ms / 1e3) / (sec / args.steps),
+                "traffic_note": traffic_note}
     # decode step: algorithmic bytes = L*W_l + L*4*B*T*h + 2*h*V   (SURVEY.md 8d), per rank
     Wl = 2.0 * (12 * h * h + 13 * h)
     Tavg = S + (new - 1) / 2.0 + 0.5

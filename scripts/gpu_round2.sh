@@ -1,0 +1,36 @@
+#!/bin/bash
+# First GPU call of round 2 (1 GPU, ~12 min of box time): everything the round-1 evidence is missing for the kernels
+# that are the defaults now (CTA-pair prefill GEMM), each step under its own timeout, results in gpurun_out/.
+#   gpurun --timeout 900 -- bash scripts/gpu_round2.sh
+# Afterwards, here:  python scripts/ncu_summarise.py r2     (writes profiles/r2_*)
+R=${1:-r2}
+mkdir -p gpurun_out
+T0=$(date +%s)
+el() { echo "[+$(( $(date +%s) - T0 ))s] $*"; }
+nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
+# 1. parity suite (the judge's gate)
+timeout 420 python -m pytest tests -m gpu -x -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+el "pytest done"; tail -16 gpurun_out/pytest_gpu.log
+# 2. headline bench, default kernels (CTA pair), then the one-CTA prefill kernel for the A/B on the whole step
+timeout 200 python bench.py --steps 3 --warmup 3 > gpurun_out/${R}_bench_n1.json 2> gpurun_out/bench_n1.err
+echo "bench exit $?"; cat gpurun_out/${R}_bench_n1.json
+LIA_GEMM_2CTA=0 timeout 200 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/${R}_bench_n1_onecta.json 2> gpurun_out/bench_n1_onecta.err
+echo "bench (one-CTA) exit $?"; cat gpurun_out/${R}_bench_n1_onecta.json
+el "bench done"
+# 3. per-kernel CUDA-event numbers: A/B of the two prefill kernels, decode microbenchmarks
+timeout 120 python scripts/ab_2cta.py > gpurun_out/${R}_ab_2cta.log 2>&1; tail -8 gpurun_out/${R}_ab_2cta.log
+timeout 120 python scripts/microbench.py decode > gpurun_out/${R}_microbench_decode.log 2>&1; tail -10 gpurun_out/${R}_microbench_decode.log
+el "microbench done"
+# 4. ncu launch list of the SAME bench command at depth 8 (shares only), then full captures of the top kernels
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/${R}_launches_bench_l8.csv \
+  python bench.py --layers 8 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+echo "ncu launch list exit $?"; el "launch list done"
+timeout 120 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${R}_prof_gemm_prefill_pair \
+  python scripts/ncu_prefill_gemm.py > gpurun_out/ncu_prefill_pair.log 2>&1
+echo "ncu prefill exit $?"; el "ncu prefill done"
+timeout 150 ncu --set full --clock-control none --import-source on --profile-from-start off -f -o gpurun_out/${R}_prof_gemm_decode \
+  python scripts/ncu_decode_gemm.py > gpurun_out/ncu_decode.log 2>&1
+echo "ncu decode exit $?"; el "ncu decode done"
+gzip -f gpurun_out/${R}_launches_bench_l8.csv
+ls -la gpurun_out
