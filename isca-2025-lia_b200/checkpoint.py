@@ -36,8 +36,11 @@ _ST_DTYPES = {"BF16": (torch.bfloat16, 2), "F16": (torch.float16, 2), "F32": (to
               "I64": (torch.int64, 8), "I32": (torch.int32, 4), "I16": (torch.int16, 2), "I8": (torch.int8, 1),
               "U8": (torch.uint8, 1), "BOOL": (torch.bool, 1)}
 _CONFIG_FIELDS = ("hidden_size", "num_hidden_layers", "num_attention_heads", "ffn_dim", "vocab_size",
-                  "max_position_embeddings", "do_layer_norm_before", "pad_token_id", "bos_token_id", "eos_token_id",
-                  "init_std")
+                  "max_position_embeddings", "do_layer_norm_before", "word_embed_proj_dim", "pad_token_id", "bos_token_id",
+                  "eos_token_id", "init_std")
+_EMBED_KEYS = {"embed_tokens": "model.decoder.embed_tokens.weight", "embed_positions": "model.decoder.embed_positions.weight",
+               "final_ln_w": "model.decoder.final_layer_norm.weight", "final_ln_b": "model.decoder.final_layer_norm.bias",
+               "project_in": "model.decoder.project_in.weight", "project_out": "model.decoder.project_out.weight"}
 
 
 class CheckpointError(RuntimeError):
@@ -195,13 +198,13 @@ def config_from_json(path):
     c = json.load(open(path))
     if c.get("model_type", "opt") != "opt":
         raise CheckpointError(f"{path}: model_type {c.get('model_type')!r} is not OPT")
-    if c.get("word_embed_proj_dim", c["hidden_size"]) != c["hidden_size"]:
-        raise NotImplementedError("word_embed_proj_dim != hidden_size (project_in/out, opt-350m only) is not on the path")
-    if not c.get("do_layer_norm_before", True):
-        raise NotImplementedError("post-LayerNorm OPT (opt-350m) is not on the path (decoder.py:250-259 is unused by LIA)")
+    if c.get("_remove_final_layer_norm", False):
+        raise NotImplementedError("_remove_final_layer_norm (pre-v4.20.1 fine-tunes, lia/modeling_opt.py:998-1001)")
     if c.get("activation_function", "relu") != "relu":
         raise NotImplementedError(f"activation {c['activation_function']!r}: OPT uses ReLU (decoder.py:92-105)")
     kw = {k: c[k] for k in _CONFIG_FIELDS if k in c and c[k] is not None}
+    if kw.get("word_embed_proj_dim") == c["hidden_size"]:
+        kw["word_embed_proj_dim"] = 0                          # 0 = "same as hidden_size"
     name = c.get("_name_or_path") or os.path.basename(os.path.dirname(os.path.abspath(path)))
     return OPTConfig(name=str(name).rstrip("/").split("/")[-1] or "opt", **kw)
 
@@ -228,12 +231,10 @@ class HFCheckpoint:
         return {k: t.to(device=device, dtype=BF16) for k, t in w.items()}
 
     def embeddings(self):
-        sd = self.sd
-        e = {"embed_tokens": sd["model.decoder.embed_tokens.weight"],
-             "embed_positions": sd["model.decoder.embed_positions.weight"],
-             "final_ln_w": sd["model.decoder.final_layer_norm.weight"],
-             "final_ln_b": sd["model.decoder.final_layer_norm.bias"]}
-        V, P = self.config.vocab_size, self.config.max_position_embeddings + 2            # offset 2, M:365-366
+        sd, cfg = self.sd, self.config
+        # final LayerNorm only for pre-LN models, project_in/out only when the token table is narrower (opt-350m)
+        e = {k: sd[name] for k, name in _EMBED_KEYS.items() if name in sd}
+        V, P = cfg.vocab_size, cfg.max_position_embeddings + 2                            # offset 2, M:365-366
         if e["embed_tokens"].shape[0] != V or e["embed_positions"].shape[0] != P:
             raise CheckpointError(f"embedding tables {tuple(e['embed_tokens'].shape)} / {tuple(e['embed_positions'].shape)} "
                                   f"do not match config (vocab {V}, positions {P})")
@@ -265,7 +266,7 @@ def write_slabs(directory, config, layer_fn, embeddings, tp_world=1):
     finally:
         for f in files:
             f.close()
-    order = ("embed_tokens", "embed_positions", "final_ln_w", "final_ln_b")
+    order = [k for k in _EMBED_KEYS if embeddings.get(k) is not None]
     emb = {}
     off = 0
     with open(os.path.join(directory, "embeddings.bin"), "wb") as f:

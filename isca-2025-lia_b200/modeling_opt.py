@@ -49,7 +49,8 @@ class OPTConfig:
     ffn_dim: int = 3072
     vocab_size: int = 50272
     max_position_embeddings: int = 2048
-    do_layer_norm_before: bool = True
+    do_layer_norm_before: bool = True  # False (opt-350m): LayerNorm AFTER each residual add, no final LayerNorm
+    word_embed_proj_dim: int = 0       # 0 = hidden_size; opt-350m embeds in 512 and projects in/out (M:985-996)
     pad_token_id: int = 1
     bos_token_id: int = 2
     eos_token_id: int = 2
@@ -63,6 +64,10 @@ class OPTConfig:
     def head_dim(self):
         return self.hidden_size // self.num_attention_heads
 
+    @property
+    def embed_dim(self):
+        return self.word_embed_proj_dim or self.hidden_size
+
 
 def _cfg(name, L, h, H, f, **kw):
     return OPTConfig(hidden_size=h, num_hidden_layers=L, num_attention_heads=H, ffn_dim=f, name=name, **kw)
@@ -71,6 +76,7 @@ def _cfg(name, L, h, H, f, **kw):
 # SURVEY.md A.1; 66b/175b from utils/opt-weight-gen.py:83-131
 OPT_CONFIGS = {
     "opt-125m": _cfg("opt-125m", 12, 768, 12, 3072),
+    "opt-350m": _cfg("opt-350m", 24, 1024, 16, 4096, do_layer_norm_before=False, word_embed_proj_dim=512),
     "opt-1.3b": _cfg("opt-1.3b", 24, 2048, 32, 8192),
     "opt-6.7b": _cfg("opt-6.7b", 32, 4096, 32, 16384),
     "opt-13b": _cfg("opt-13b", 40, 5120, 40, 20480),
@@ -114,8 +120,11 @@ class _Workspace:
         self.x1d = e(batch, h) if (arena is not None and os.environ.get("LIA_TP_DECODE_ARENA", "0") == "0") else self.x1
         self.tp = e(rows, h) if layout.tp > 1 and arena is None else None
         shapes = []
+        e_dim = cfg.embed_dim
         for m in {rows, batch}:
-            shapes += [(m, 3 * hq, h), (m, h, hq), (m, fq, h), (m, h, fq), (m, cfg.vocab_size, h)]
+            shapes += [(m, 3 * hq, h), (m, h, hq), (m, fq, h), (m, h, fq), (m, cfg.vocab_size, e_dim)]
+            if e_dim != h:
+                shapes += [(m, h, e_dim), (m, e_dim, h)]                   # project_in / project_out
         self.gemm = ops.GemmWorkspace(ops.GemmWorkspace.bytes_for(shapes), device)
         self.attn = ops.attn_decode_workspace(batch, cfg.num_attention_heads // layout.tp, cfg.head_dim, device)
 
@@ -201,7 +210,7 @@ class OPTDecoderLayer:
 
     def __init__(self, decoder, idx):
         self.decoder, self.idx = decoder, idx
-        self.do_layer_norm_before = True
+        self.do_layer_norm_before = decoder.config.do_layer_norm_before          # M:778
         self.distributed = decoder.tp_world > 1
 
     # ---- the reference's layer face
@@ -264,6 +273,8 @@ class OPTDecoder:
         self.layers = [OPTDecoderLayer(self, i) for i in range(config.num_hidden_layers)]
         self.scaling = config.head_dim ** -0.5                      # lia/modeling_opt.py:413
         self.embed_tokens = self.embed_positions = self.final_ln_w = self.final_ln_b = None
+        self.project_in = self.project_out = None      # [h, e] / [e, h], only when word_embed_proj_dim != hidden_size
+        self.pre_ln = bool(config.do_layer_norm_before)
         self.n_resident = 0
         self.resident = []          # flat device slabs
         self.resident_views = []
@@ -334,11 +345,49 @@ class OPTDecoder:
             self.streamer = LayerStreamer(self.layout, self.host_slabs, self.device)
 
     def load_embeddings(self, e):
-        dev = self.device
-        self.embed_tokens = e["embed_tokens"].to(dev, BF16).contiguous()
-        self.embed_positions = e["embed_positions"].to(dev, BF16).contiguous()
-        self.final_ln_w = e["final_ln_w"].to(dev, BF16).contiguous()
-        self.final_ln_b = e["final_ln_b"].to(dev, BF16).contiguous()
+        dev, cfg = self.device, self.config
+        put = lambda t: None if t is None else t.to(dev, BF16).contiguous()  # noqa: E731
+        self.embed_tokens = put(e["embed_tokens"])
+        self.embed_positions = put(e["embed_positions"])
+        # M:1001-1006: the final LayerNorm exists only for pre-LN models
+        self.final_ln_w, self.final_ln_b = put(e.get("final_ln_w")), put(e.get("final_ln_b"))
+        if self.pre_ln != (self.final_ln_w is not None):
+            raise ValueError(f"do_layer_norm_before={self.pre_ln} but the checkpoint "
+                             f"{'has no' if self.pre_ln else 'has a'} final LayerNorm")
+        # M:988-996: project_in / project_out (bias-free) either side of the stack when the tables are narrower
+        self.project_in, self.project_out = put(e.get("project_in")), put(e.get("project_out"))
+        h, ed = cfg.hidden_size, cfg.embed_dim
+        if (ed != h) != (self.project_in is not None and self.project_out is not None):
+            raise ValueError(f"word_embed_proj_dim {ed} vs hidden_size {h}: project_in/project_out "
+                             f"{'missing' if ed != h else 'unexpected'}")
+        if tuple(self.embed_tokens.shape) != (cfg.vocab_size, ed) or self.embed_positions.shape[1] != h:
+            raise ValueError(f"embedding tables {tuple(self.embed_tokens.shape)} / {tuple(self.embed_positions.shape)} do not "
+                             f"match vocab {cfg.vocab_size}, word_embed_proj_dim {ed}, hidden_size {h}")
+        if ed != h:
+            # one-row zero tables: the embed kernel clamps out-of-range ids / positions to the last row, so a lookup
+            # against them contributes +0 and the kernel returns the other table's rows unchanged
+            self._zero_tok = torch.zeros(1, h, dtype=BF16, device=dev)
+            self._zero_pos = torch.zeros(1, ed, dtype=BF16, device=dev)
+
+    def embed_rows(self, ids, past_len, mask, out, ws):
+        """hidden = project_in(embed_tokens[ids]) + embed_positions[pos]  (M:1107-1142) into ``out`` [B,S,h]."""
+        if self.project_in is None:
+            return ops.embed(ids, self.embed_tokens, self.embed_positions, past_len, out=out, attention_mask=mask)
+        B, S = ids.shape
+        h, ed = self.config.hidden_size, self.config.embed_dim
+        tok = ops.embed(ids, self.embed_tokens, self._zero_pos, past_len, attention_mask=mask)     # token rows [B,S,e]
+        pos = ops.embed(ids, self._zero_tok, self.embed_positions, past_len, attention_mask=mask)  # position rows [B,S,h]
+        ops.gemm(tok.view(B * S, ed), self.project_in, None, out=out.view(B * S, h), epilogue=EPI_BIAS_RESIDUAL,
+                 residual=pos.view(B * S, h), workspace=ws.gemm)                                   # M:1139-1142
+        return out
+
+    def final_rows(self, rows, ws, out=None):
+        """Final LayerNorm (pre-LN models, M:1563-1564) and project_out (M:1566-1567) over ``rows`` [M,h]."""
+        if self.final_ln_w is not None:
+            rows = ops.layernorm(rows, self.final_ln_w, self.final_ln_b, LN_EPS, out=out)
+        if self.project_out is not None:
+            rows = ops.gemm(rows, self.project_out, None, epilogue=EPI_BIAS, workspace=ws.gemm)
+        return rows
 
     def check_gpu_percentage(self, gpu_percentage):
         if gpu_percentage is None:
@@ -361,39 +410,45 @@ class OPTDecoder:
         return self._ws[key]
 
     # ---- one layer over a block of token rows (rows are [b-major, S] and updated in place)
+    def _row_parallel(self, a, w, b, residual, out, ws, big):
+        """out = residual + (a . w^T + b), summed over the tensor-parallel ranks (out_proj D:222-247, fc2 D:302-317)."""
+        arena = ws.arena
+        if self.tp_world == 1:
+            ops.gemm(a, w, b, out=out, epilogue=EPI_BIAS_RESIDUAL, residual=residual, workspace=ws.gemm)   # D:228-229, 309-310
+        elif arena is not None:             # D:60-68 + 247/317 as one kernel over NVLink peer memory
+            # prefill tiles are finished by their owner rank, which writes `out` remotely: it must live in the arena
+            ops.gemm_allreduce(a, w, b, residual, out, arena.args(out if big else None), workspace=ws.gemm)
+        else:
+            part = ws.tp[:a.shape[0]]
+            ops.gemm(a, w, b, out=part, epilogue=EPI_BIAS, workspace=ws.gemm)                              # D:60-68
+            tp_mod.all_reduce(part)
+            ops.residual_add(part, residual, out=out)                                                      # D:247, 317
+
     def layer_rows(self, v, rows, kc, vc, nb, S, pos0, b0, ws):
         M = nb * S
         ln, q, ctx, ffn = ws.ln[:M], ws.q[:M], ws.ctx[:M], ws.ffn[:M]
-        x1 = ws.x1[:M] if M > 128 else ws.x1d[:M]
-        ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                   # decoder.py:204
-        ops.gemm(ln, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                                        # attentions.py:376-491
+        big = M > 128
+        x1 = ws.x1[:M] if big else ws.x1d[:M]
+        pre = self.pre_ln
+        if pre:
+            ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                               # decoder.py:198-204
+        ops.gemm(ln if pre else rows, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                       # attentions.py:376-491
                  qkv=ops.qkv_args(q, kc, vc, S, pos0, b0, self.scaling), workspace=ws.gemm)
         if S != 1:
             ops.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
         else:
             ops.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
-        arena = ws.arena
-        big = M > 128                       # prefill tiles are finished by their owner rank, which writes `out` remotely
-        if self.tp_world == 1:
-            ops.gemm(ctx, v["o_w"], v["o_b"], out=x1, epilogue=EPI_BIAS_RESIDUAL, residual=rows, workspace=ws.gemm)  # decoder.py:228-229
-        elif arena is not None:             # decoder.py:60-68 + 247 as one kernel over NVLink peer memory
-            ops.gemm_allreduce(ctx, v["o_w"], v["o_b"], rows, x1, arena.args(x1 if big else None), workspace=ws.gemm)
+        self._row_parallel(ctx, v["o_w"], v["o_b"], rows, x1, ws, big)                                # decoder.py:222-247
+        if pre:
+            ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                 # decoder.py:266-272
+            ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
+            self._row_parallel(ffn, v["fc2_w"], v["fc2_b"], x1, rows, ws, big)                        # decoder.py:302-317
         else:
-            part = ws.tp[:M]
-            ops.gemm(ctx, v["o_w"], v["o_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)        # decoder.py:60-68
-            tp_mod.all_reduce(part)
-            ops.residual_add(part, rows, out=x1)                                                      # decoder.py:247
-        ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                     # decoder.py:272
-        ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)      # decoder.py:285
-        if self.tp_world == 1:
-            ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=rows, epilogue=EPI_BIAS_RESIDUAL, residual=x1, workspace=ws.gemm)  # decoder.py:309-310
-        elif arena is not None:             # decoder.py:316-317
-            ops.gemm_allreduce(ffn, v["fc2_w"], v["fc2_b"], x1, rows, arena.args(rows if big else None), workspace=ws.gemm)
-        else:
-            part = ws.tp[:M]
-            ops.gemm(ffn, v["fc2_w"], v["fc2_b"], out=part, epilogue=EPI_BIAS, workspace=ws.gemm)
-            tp_mod.all_reduce(part)
-            ops.residual_add(part, x1, out=rows)                                                      # decoder.py:317
+            # opt-350m: LayerNorm follows each residual add; its output is both the MLP input and the next residual
+            ops.layernorm(x1, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                 # decoder.py:250-256
+            ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
+            self._row_parallel(ffn, v["fc2_w"], v["fc2_b"], ln, x1, ws, big)                          # decoder.py:302-317
+            ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=rows)                               # decoder.py:320-321
 
     def run_layers(self, x, kcs, vcs, B, S, pos0, num_minibatch, ws, spill=None):
         """Layer-major, minibatch-minor loop (lia/modeling_opt.py:1222, 1284) with double-buffered
@@ -452,10 +507,10 @@ class OPTDecoder:
         am = None
         if attention_mask is not None:                 # only the learned positions depend on it (M:368-378; A:446-449, A:500)
             am = attention_mask.to(self.device, torch.int64).contiguous()
-        x = ops.embed(ids, self.embed_tokens, self.embed_positions, past_len,
-                      attention_mask=am).view(B * S, cfg.hidden_size)                                          # M:1107-1142
+        x = torch.empty(B * S, cfg.hidden_size, dtype=BF16, device=self.device)
+        self.embed_rows(ids, past_len, am, x.view(B, S, cfg.hidden_size), ws)                                  # M:1107-1142
         self.run_layers(x, kcs, vcs, B, S, past_len, num_minibatch, ws)
-        hidden = ops.layernorm(x, self.final_ln_w, self.final_ln_b, LN_EPS).view(B, S, cfg.hidden_size)       # M:1563-1564
+        hidden = self.final_rows(x, ws).view(B, S, cfg.embed_dim)                                              # M:1563-1567
         T = past_len + S
         marker = torch.empty(1, T, T, 1, dtype=torch.long, device="meta")
         next_cache = tuple((marker, k, v, beam) for k, v in zip(kcs, vcs))
@@ -491,7 +546,8 @@ class OPTForCausalLM:
         cfg = self.config
         dec = self.model.decoder
         dec.load_embeddings(random_embeddings(cfg.vocab_size, cfg.hidden_size, cfg.max_position_embeddings,
-                                              seed * 100003 + 17, self.device, kind, cfg.init_std, ln_std, cfg.pad_token_id))
+                                              seed * 100003 + 17, self.device, kind, cfg.init_std, ln_std, cfg.pad_token_id,
+                                              embed_dim=cfg.embed_dim, final_ln=cfg.do_layer_norm_before))
         dec.load_layers(lambda i, dev: random_layer(cfg.hidden_size, cfg.ffn_dim, seed * 100003 + 1000 + i, dev, kind,
                                                     cfg.init_std, bias_std, ln_std), gpu_percentage)
         return self
@@ -501,8 +557,10 @@ class OPTForCausalLM:
         dec = self.model.decoder
         dec.load_embeddings({"embed_tokens": sd["model.decoder.embed_tokens.weight"],
                              "embed_positions": sd["model.decoder.embed_positions.weight"],
-                             "final_ln_w": sd["model.decoder.final_layer_norm.weight"],
-                             "final_ln_b": sd["model.decoder.final_layer_norm.bias"]})
+                             "final_ln_w": sd.get("model.decoder.final_layer_norm.weight"),
+                             "final_ln_b": sd.get("model.decoder.final_layer_norm.bias"),
+                             "project_in": sd.get("model.decoder.project_in.weight"),
+                             "project_out": sd.get("model.decoder.project_out.weight")})
         dec.load_layers(lambda i, dev: {k: t.to(dev, BF16) for k, t in layer_from_hf_state_dict(sd, i).items()},
                         gpu_percentage)
         return self
@@ -548,8 +606,8 @@ class OPTForCausalLM:
             enable_cxl=enable_cxl, max_new_tokens=max_new_tokens)
         if self.config.lm_head_generation and hidden.size(1) != 1:                       # models.py:424-431
             hidden = hidden[:, -1:, :]
-        B, S, h = hidden.shape
-        logits = self.lm_head(hidden.reshape(B * S, h).contiguous()).view(B, S, self.config.vocab_size)
+        B, S, e = hidden.shape                                                            # e = word_embed_proj_dim
+        logits = self.lm_head(hidden.reshape(B * S, e).contiguous()).view(B, S, self.config.vocab_size)
         return (logits, cache)
 
     __call__ = forward
@@ -572,15 +630,14 @@ class OPTForCausalLM:
 
     def _head_and_pick(self, st, rows, t, suppress):
         dec = self.model.decoder
-        ops.layernorm(rows, dec.final_ln_w, dec.final_ln_b, LN_EPS, out=st.xn)           # M:1563-1564 (last position)
-        self.lm_head(st.xn, out=st.logits, ws=st.ws)                                      # models.py:431
+        xn = dec.final_rows(rows, st.ws, out=st.xn)                                       # M:1563-1567 (last position)
+        self.lm_head(xn, out=st.logits, ws=st.ws)                                         # models.py:431
         ops.argmax(st.logits, suppress, out=st.steps_tok[t])                              # greedy_search.py:367-395
 
     def _prefill(self, st, num_minibatch, suppress):
         dec, cfg = self.model.decoder, self.config
         B, S = st.B, st.S
-        ops.embed(st.prompt, dec.embed_tokens, dec.embed_positions, 0, out=st.x.view(B, S, cfg.hidden_size),
-                  attention_mask=st.mask)
+        dec.embed_rows(st.prompt, 0, st.mask, st.x.view(B, S, cfg.hidden_size), st.ws)
         dec.run_layers(st.x, st.kc, st.vc, B, S, 0, num_minibatch, st.ws, st.spill)
         st.xd.copy_(st.x.view(B, S, cfg.hidden_size)[:, -1, :])                           # models.py:430 last token only
         self._head_and_pick(st, st.xd, 0, suppress)
@@ -589,8 +646,7 @@ class OPTForCausalLM:
         """Generate token t (>= 1) from token t-1; cache holds S + t - 1 positions."""
         dec, cfg = self.model.decoder, self.config
         past = st.S + t - 1
-        ops.embed(st.steps_tok[t - 1].view(st.B, 1), dec.embed_tokens, dec.embed_positions, past,
-                  out=st.xd.view(st.B, 1, cfg.hidden_size), attention_mask=st.mask)
+        dec.embed_rows(st.steps_tok[t - 1].view(st.B, 1), past, st.mask, st.xd.view(st.B, 1, cfg.hidden_size), st.ws)
         dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws, st.spill)
         self._head_and_pick(st, st.xd, t, suppress)
 

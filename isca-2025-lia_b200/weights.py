@@ -120,22 +120,34 @@ def random_layer(h, f, seed, device="cpu", kind="normal", std=0.02, bias_std=0.0
     return w
 
 
-def random_embeddings(vocab, h, max_pos, seed, device="cpu", kind="normal", std=0.02, ln_std=0.0, pad_id=1):
-    """embed_tokens [V,h] (padding row zeroed, lia/modeling_opt.py:900-904), embed_positions
-    [max_pos+2, h] (offset 2, :365-366), final LayerNorm."""
+def random_embeddings(vocab, h, max_pos, seed, device="cpu", kind="normal", std=0.02, ln_std=0.0, pad_id=1, embed_dim=None,
+                      final_ln=True):
+    """embed_tokens [V,e] (padding row zeroed, lia/modeling_opt.py:900-904), embed_positions
+    [max_pos+2, h] (offset 2, :365-366), final LayerNorm (pre-LN models only, :1001-1006) and, when the token
+    table is narrower than the model (e != h: opt-350m, :988-996), bias-free project_in [h,e] / project_out [e,h].
+    The generator is consumed in the same order as before for e == h, so existing seeds give the same weights."""
     g = torch.Generator(device=device).manual_seed(seed)
+    e_dim = embed_dim or h
     if kind == "dummy":
         r = lambda *s: torch.rand(*s, generator=g, device=device, dtype=torch.float32).to(BF16)  # noqa: E731
-        return {"embed_tokens": r(vocab, h), "embed_positions": r(max_pos + 2, h), "final_ln_w": r(h), "final_ln_b": r(h)}
+        e = {"embed_tokens": r(vocab, e_dim), "embed_positions": r(max_pos + 2, h)}
+        if final_ln:
+            e["final_ln_w"], e["final_ln_b"] = r(h), r(h)
+        if e_dim != h:
+            e["project_in"], e["project_out"] = r(h, e_dim), r(e_dim, h)
+        return e
     n = lambda *s: (torch.randn(*s, generator=g, device=device, dtype=torch.float32) * std).to(BF16)  # noqa: E731
-    e = {"embed_tokens": n(vocab, h), "embed_positions": n(max_pos + 2, h)}
+    e = {"embed_tokens": n(vocab, e_dim), "embed_positions": n(max_pos + 2, h)}
     e["embed_tokens"][pad_id].zero_()
-    if ln_std > 0:
-        e["final_ln_w"] = (1 + torch.randn(h, generator=g, device=device) * ln_std).to(BF16)
-        e["final_ln_b"] = (torch.randn(h, generator=g, device=device) * ln_std).to(BF16)
-    else:
-        e["final_ln_w"] = torch.ones(h, dtype=BF16, device=device)
-        e["final_ln_b"] = torch.zeros(h, dtype=BF16, device=device)
+    if final_ln:
+        if ln_std > 0:
+            e["final_ln_w"] = (1 + torch.randn(h, generator=g, device=device) * ln_std).to(BF16)
+            e["final_ln_b"] = (torch.randn(h, generator=g, device=device) * ln_std).to(BF16)
+        else:
+            e["final_ln_w"] = torch.ones(h, dtype=BF16, device=device)
+            e["final_ln_b"] = torch.zeros(h, dtype=BF16, device=device)
+    if e_dim != h:
+        e["project_in"], e["project_out"] = n(h, e_dim), n(e_dim, h)
     return e
 
 

@@ -99,7 +99,7 @@ class _Holder:
     pass
 
 
-def build_reference_layer(w, h, H):
+def build_reference_layer(w, h, H, pre_ln=True):
     """Fake ``self`` objects carrying exactly the attributes the two lifted
     functions read on the policy-3 path (names as set up by
     _IPEXDecoderLayerRef.__init__, decoder.py:1385-1392, and by
@@ -128,7 +128,7 @@ def build_reference_layer(w, h, H):
 
     layer = _Holder()
     layer.distributed = False
-    layer.do_layer_norm_before = True
+    layer.do_layer_norm_before = pre_ln                     # False: opt-350m (decoder.py:250-259, 320-321)
     layer.self_attn_layer_norm = ln(w["ln1_w"], w["ln1_b"])
     layer.final_layer_norm = ln(w["ln2_w"], w["ln2_b"])
     layer.mha_linear_add = _Holder(); layer.mha_linear_add.weight = w["o_w"]; layer.mha_linear_add.bias = w["o_b"]
@@ -145,17 +145,17 @@ def build_reference_layer(w, h, H):
     return call
 
 
-def gen_layer_case(name, B, S, h, H, new, seed):
+def gen_layer_case(name, B, S, h, H, new, seed, pre_ln=True):
     f = 4 * h
     w = make_layer_weights(h, f, seed)
-    call = build_reference_layer(w, h, H)
+    call = build_reference_layer(w, h, H, pre_ln)
     g = torch.Generator().manual_seed(seed + 1000)
     xs = [torch.randn(B, S, h, generator=g).to(torch.bfloat16)]
     xs += [torch.randn(B, 1, h, generator=g).to(torch.bfloat16) for _ in range(new)]
     # initial fake past: intel_extension_for_pytorch/transformers/generation/greedy_search.py:272-282
     past = (torch.zeros(1, 0, 0, 1, dtype=torch.long), torch.zeros(1, 1, 1, 1), torch.zeros(1, 1, 1, 1),
             torch.zeros(2048, B, dtype=torch.long))
-    out = {"B": B, "S": S, "h": h, "H": H, "new": new, "seed": seed}
+    out = {"B": B, "S": S, "h": h, "H": H, "new": new, "seed": seed, "pre_ln": int(pre_ln)}
     for k, v in w.items():
         out["w_" + k] = bf16_bits(v)
     for step, x in enumerate(xs):
@@ -170,12 +170,12 @@ def gen_layer_case(name, B, S, h, H, new, seed):
     print("wrote", name, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
-def gen_hf_model_case(name, V, h, H, L, P, B, S, new, seed):
+def gen_hf_model_case(name, V, h, H, L, P, B, S, new, seed, word_dim=None, pre_ln=True):
     from transformers import OPTConfig, OPTForCausalLM
     torch.manual_seed(seed)
     cfg = OPTConfig(vocab_size=V, hidden_size=h, num_attention_heads=H, num_hidden_layers=L,
-                    ffn_dim=4 * h, max_position_embeddings=P, word_embed_proj_dim=h,
-                    do_layer_norm_before=True, activation_function="relu", dropout=0.0,
+                    ffn_dim=4 * h, max_position_embeddings=P, word_embed_proj_dim=word_dim or h,
+                    do_layer_norm_before=pre_ln, activation_function="relu", dropout=0.0,
                     pad_token_id=1, bos_token_id=2, eos_token_id=2, init_std=0.02)
     model = OPTForCausalLM(cfg).eval().float()
     # make every parameter exactly bf16-representable so that the fixture can be stored as bf16 bits
@@ -194,8 +194,8 @@ def gen_hf_model_case(name, V, h, H, L, P, B, S, new, seed):
     with torch.no_grad():
         logits = model(ids).logits[:, -1, :]
         toks = model.generate(ids, do_sample=False, num_beams=1, max_new_tokens=new, min_new_tokens=new)
-    out = {"V": V, "h": h, "H": H, "L": L, "P": P, "B": B, "S": S, "new": new,
-           "input_ids": ids.numpy(), "prefill_last_logits": logits.numpy().astype(np.float32),
+    out = {"V": V, "h": h, "H": H, "L": L, "P": P, "B": B, "S": S, "new": new, "word_dim": word_dim or h,
+           "pre_ln": int(pre_ln), "input_ids": ids.numpy(), "prefill_last_logits": logits.numpy().astype(np.float32),
            "tokens": toks.numpy()}
     sd = model.state_dict()
     for k, v in sd.items():
@@ -273,6 +273,9 @@ def main():
     gen_layer_case("layer_ragged", B=1, S=1 + 16, h=192, H=3, new=1, seed=13)   # h not a power of two
     gen_positions_case("positions_padded", seed=31)
     gen_hf_model_case("model_hf_tiny", V=320, h=64, H=1, L=2, P=48, B=3, S=7, new=5, seed=21)
+    # opt-350m's shape of model: LayerNorm after the residual adds, no final LayerNorm, project_in / project_out
+    gen_layer_case("layer_postln", B=2, S=6, h=128, H=2, new=2, seed=14, pre_ln=False)
+    gen_hf_model_case("model_hf_postln_tiny", V=320, h=128, H=2, L=2, P=48, B=3, S=7, new=5, seed=22, word_dim=64, pre_ln=False)
 
 
 if __name__ == "__main__":

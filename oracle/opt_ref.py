@@ -93,22 +93,32 @@ def attention_forward(x, w, H, kcache, vcache, cur_len):
     return ctx
 
 
-def layer_forward(x, w, H, kcache, vcache, cur_len):
-    """D:172-335 with policy 3, non-distributed, ``do_layer_norm_before``.
+def layer_forward(x, w, H, kcache, vcache, cur_len, pre_ln=True):
+    """D:172-335 with policy 3, non-distributed.  ``pre_ln`` is ``do_layer_norm_before``: True for every OPT
+    size except opt-350m, whose LayerNorms follow the residual adds instead (D:250-259, D:320-321).
 
     Returns the new hidden state [B,S,h]; caches are updated in place.
     """
     h = x.shape[-1]
     residual = x                                                          # D:195
-    y = F.layer_norm(x, (h,), w["ln1_w"], w["ln1_b"], LN_EPS)             # D:204 -> D:107-112
+    y = x
+    if pre_ln:
+        y = F.layer_norm(y, (h,), w["ln1_w"], w["ln1_b"], LN_EPS)         # D:198-204 -> D:107-112
     y = attention_forward(y, w, H, kcache, vcache, cur_len)              # D:210-220
     y = _linear(y, w["o_w"], w["o_b"]).contiguous()                      # D:228 -> D:86-90
     y = residual + y                                                      # D:229
+    if not pre_ln:
+        y = F.layer_norm(y, (h,), w["ln1_w"], w["ln1_b"], LN_EPS)         # D:250-256 -> D:107-112
     residual = y                                                          # D:264
-    z = F.layer_norm(y, (h,), w["ln2_w"], w["ln2_b"], LN_EPS)             # D:272 -> D:114-119
+    z = y
+    if pre_ln:
+        z = F.layer_norm(z, (h,), w["ln2_w"], w["ln2_b"], LN_EPS)         # D:266-272 -> D:114-119
     z = F.relu(_linear(z, w["fc1_w"], w["fc1_b"]).contiguous())          # D:285 -> D:100-105
     z = _linear(z, w["fc2_w"], w["fc2_b"]).contiguous()                  # D:309
-    return (residual + z).view(x.shape)                                  # D:310
+    out = (residual + z).view(x.shape)                                   # D:310
+    if not pre_ln:
+        out = F.layer_norm(out, (h,), w["ln2_w"], w["ln2_b"], LN_EPS)     # D:320-321 (the nn.LayerNorm module itself)
+    return out
 
 
 # --------------------------------------------------------------------------- whole model
@@ -121,15 +131,18 @@ def positions_from_mask(attention_mask, past_len):
 
 
 def embed(model, input_ids, attention_mask, past_len):
-    """M:1107-1142: token embedding + learned positional embedding (no project_in)."""
+    """M:1107-1142: token embedding (+ ``project_in`` when word_embed_proj_dim != hidden_size, M:1139-1140:
+    opt-350m only) + learned positional embedding."""
     tok = F.embedding(input_ids, model["embed_tokens"])
     pos = F.embedding(positions_from_mask(attention_mask, past_len), model["embed_positions"])
+    if model.get("project_in") is not None:
+        tok = torch.matmul(tok, model["project_in"].t())                  # nn.Linear(bias=False), M:994
     return tok + pos
 
 
 def new_cache(model, B, Tmax, device=None, dtype=None):
     """Per-layer time-major KV cache [(S+new), B, H, d] (A:471-472, M:1277-1278)."""
-    e = model["embed_tokens"]
+    e = model["embed_positions"]          # [P+2, hidden]; embed_tokens is [V, word_embed_proj_dim]
     h, H = e.shape[1], model["H"]
     device = device or e.device
     dtype = dtype or e.dtype
@@ -142,12 +155,17 @@ def decoder_forward(model, input_ids, attention_mask, cache, past_len, collect=N
     (per-layer dispatch M:1246-1260; final LN M:1563-1564).  ``collect``, if a
     list, receives every layer's output hidden state."""
     x = embed(model, input_ids, attention_mask, past_len)
+    pre_ln = model.get("pre_ln", True)
     for li, w in enumerate(model["layers"]):
-        x = layer_forward(x, w, model["H"], cache[li][0], cache[li][1], past_len)
+        x = layer_forward(x, w, model["H"], cache[li][0], cache[li][1], past_len, pre_ln)
         if collect is not None:
             collect.append(x)
     h = x.shape[-1]
-    return F.layer_norm(x, (h,), model["final_ln_w"], model["final_ln_b"], LN_EPS)
+    if model.get("final_ln_w") is not None:                               # M:1001-1006: absent when not pre-LN
+        x = F.layer_norm(x, (h,), model["final_ln_w"], model["final_ln_b"], LN_EPS)   # M:1563-1564
+    if model.get("project_out") is not None:
+        x = torch.matmul(x, model["project_out"].t())                     # M:1566-1567
+    return x
 
 
 def lm_logits(model, hidden):
@@ -307,8 +325,12 @@ def model_from_hf_state_dict(sd, H):
     return {"H": H, "layers": layers,
             "embed_tokens": sd["model.decoder.embed_tokens.weight"],
             "embed_positions": sd["model.decoder.embed_positions.weight"],
-            "final_ln_w": sd["model.decoder.final_layer_norm.weight"],
-            "final_ln_b": sd["model.decoder.final_layer_norm.bias"]}
+            # opt-350m: no final LayerNorm (M:1001-1006), LayerNorm after the residual adds, and a projection either side
+            "pre_ln": "model.decoder.final_layer_norm.weight" in sd,
+            "final_ln_w": sd.get("model.decoder.final_layer_norm.weight"),
+            "final_ln_b": sd.get("model.decoder.final_layer_norm.bias"),
+            "project_in": sd.get("model.decoder.project_in.weight"),
+            "project_out": sd.get("model.decoder.project_out.weight")}
 
 
 def model_to(model, device=None, dtype=None):

@@ -149,7 +149,7 @@ def test_native_slab_round_trip(tmp_path, world):
 def test_unsupported_architectures_are_refused(tmp_path):
     base = dict(model_type="opt", hidden_size=64, num_hidden_layers=1, num_attention_heads=1, ffn_dim=128, vocab_size=96,
                 max_position_embeddings=32)
-    for extra, exc in (({"word_embed_proj_dim": 32}, NotImplementedError), ({"do_layer_norm_before": False}, NotImplementedError),
+    for extra, exc in (({"_remove_final_layer_norm": True}, NotImplementedError),
                        ({"activation_function": "gelu"}, NotImplementedError), ({"model_type": "llama"}, checkpoint.CheckpointError)):
         json.dump({**base, **extra}, open(tmp_path / "config.json", "w"))
         with pytest.raises(exc):
@@ -159,6 +159,32 @@ def test_unsupported_architectures_are_refused(tmp_path):
     json.dump(base, open(tmp_path / "config.json", "w"))
     with pytest.raises(checkpoint.CheckpointError, match="no model.safetensors"):
         checkpoint.open_checkpoint(str(tmp_path))
+
+
+def test_opt350m_shaped_checkpoint_round_trip(tmp_path):
+    """opt-350m's architecture (LayerNorm after the residual adds, no final LayerNorm, project_in/out around a narrower
+    token table; lia/modeling_opt.py:985-1006): HF directory -> config + embeddings -> native slabs -> same tensors."""
+    from transformers import OPTConfig as HFConfig, OPTForCausalLM as HFOPT
+    torch.manual_seed(1)
+    c = HFConfig(vocab_size=96, hidden_size=64, num_hidden_layers=2, num_attention_heads=1, ffn_dim=128,
+                 max_position_embeddings=32, word_embed_proj_dim=32, do_layer_norm_before=False)
+    m = HFOPT(c).eval().to(BF16)
+    src, dst = tmp_path / "hf", tmp_path / "slabs"
+    m.save_pretrained(str(src), safe_serialization=True)
+    ck = checkpoint.open_checkpoint(str(src))
+    assert ck.config.word_embed_proj_dim == 32 and ck.config.embed_dim == 32 and ck.config.do_layer_norm_before is False
+    e = ck.embeddings()
+    assert set(e) == {"embed_tokens", "embed_positions", "project_in", "project_out"}
+    assert e["embed_tokens"].shape == (96, 32) and e["project_in"].shape == (64, 32) and e["project_out"].shape == (32, 64)
+    checkpoint.convert(str(src), str(dst))
+    nk = checkpoint.open_checkpoint(str(dst))
+    assert nk.config.word_embed_proj_dim == 32 and nk.config.do_layer_norm_before is False
+    e2 = nk.embeddings()
+    assert set(e2) == set(e) and all(torch.equal(e[k], e2[k]) for k in e)
+    nk.close()
+    # a pre-LN model with equal widths keeps word_embed_proj_dim == 0 ("same as hidden_size")
+    tiny_hf_model().save_pretrained(str(tmp_path / "plain"), safe_serialization=True)
+    assert checkpoint.open_checkpoint(str(tmp_path / "plain")).config.word_embed_proj_dim == 0
 
 
 def test_weight_gen_script_writes_dummy_slabs(tmp_path):

@@ -1,0 +1,202 @@
+"""HOST logic of the model surface on CPU: ``modeling_opt`` driven through a stock-PyTorch stand-in for the kernel layer
+(tests/cpu_ops_emulation.py -- test infrastructure) and compared BIT FOR BIT with the oracle and with the goldens made
+from the reference's own layer code.  What this pins without a GPU: the order and operands of the seven launches of a
+layer, the minibatch loop and its cache windows, the KV-cache / past_key_values bookkeeping, learned positions under
+padding, the last-token head, eos suppression and the token matrix of the greedy loop, and the three reference faces
+(layer, decoder, model).  The kernels themselves are checked on the GPU (tests/test_gpu_*.py)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import lia_b200  # noqa: E402
+from oracle import opt_ref  # noqa: E402
+from cpu_ops_emulation import cpu_ops  # noqa: E402,F401  (fixture)
+from test_oracle_golden import LAYER_CASES, load_layer_case  # noqa: E402
+
+BF16 = torch.bfloat16
+
+
+def oracle_model(m):
+    """Oracle model dict over the SAME weights as the product model ``m`` (unfused q/k/v views of its slabs)."""
+    dec = m.model.decoder
+    hq = dec.layout.hq
+    layers = []
+    for v in dec.resident_views:
+        w = {k: v[k] for k in ("ln1_w", "ln1_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")}
+        w["q_w"], w["k_w"], w["v_w"] = v["qkv_w"][:hq], v["qkv_w"][hq:2 * hq], v["qkv_w"][2 * hq:]
+        w["q_b"], w["k_b"], w["v_b"] = v["qkv_b"][:hq], v["qkv_b"][hq:2 * hq], v["qkv_b"][2 * hq:]
+        layers.append(w)
+    om = {"H": m.config.num_attention_heads, "layers": layers, "embed_tokens": dec.embed_tokens,
+          "embed_positions": dec.embed_positions, "final_ln_w": dec.final_ln_w, "final_ln_b": dec.final_ln_b,
+          "pre_ln": m.config.do_layer_norm_before}
+    for k in ("project_in", "project_out"):
+        om[k] = getattr(dec, k, None)
+    return om
+
+
+def tiny(**kw):
+    base = dict(hidden_size=128, num_hidden_layers=3, num_attention_heads=2, ffn_dim=512, vocab_size=384, max_position_embeddings=64)
+    base.update(kw)
+    cfg = lia_b200.OPTConfig(**base)
+    m = lia_b200.OPTForCausalLM(cfg, "cpu").init_weights(seed=4, bias_std=0.05, ln_std=0.1)
+    m.use_cuda_graphs = False
+    return cfg, m
+
+
+@pytest.mark.parametrize("num_minibatch", [1, 2, 3])
+def test_generate_matches_oracle_bit_for_bit(cpu_ops, num_minibatch):
+    cfg, m = tiny()
+    B, S, new = 6, 9, 5
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(1))
+    toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new, prefill_policy=0, decoding_policy=0, num_minibatch=num_minibatch)
+    with torch.no_grad():
+        ref = opt_ref.greedy_generate(oracle_model(m), ids, new)
+    assert torch.equal(toks, ref)
+    # cache rows of every layer equal the oracle's (time-major [T, B, H, d], A:471-472)
+    st = next(iter(m._states.values()))
+    cache = opt_ref.new_cache(oracle_model(m), B, S + new)
+    with torch.no_grad():
+        hid = opt_ref.decoder_forward(oracle_model(m), ids, torch.ones(B, S, dtype=torch.long), cache, 0)
+    for li in range(cfg.num_hidden_layers):
+        assert torch.equal(st.kc[li][:S], cache[li][0][:S]) and torch.equal(st.vc[li][:S], cache[li][1][:S])
+    # launch sequence of one layer in prefill: LN, fused QKV, attention, out_proj(+res), LN, fc1(+relu), fc2(+res)
+    names = [c for c in cpu_ops.log if c[0] != "embed"][:7]
+    assert [c[0] for c in names] == ["layernorm", "gemm", "attn_prefill", "gemm", "layernorm", "gemm", "gemm"]
+    assert [c[1] for c in names if c[0] == "gemm"] == [3, 2, 1, 2]          # QKV, BIAS_RESIDUAL, BIAS_RELU, BIAS_RESIDUAL
+    assert hid.shape == (B, S, cfg.hidden_size)
+
+
+def test_generate_padded_prompt_and_eos_suppression(cpu_ops):
+    cfg, m = tiny()
+    B, S, new = 4, 8, 4
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(2))
+    ids[0, :3] = cfg.pad_token_id          # left padding moves the learned positions (M:368-378)
+    ids[1, -2:] = cfg.pad_token_id
+    toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new)
+    with torch.no_grad():
+        ref = opt_ref.greedy_generate(oracle_model(m), ids, new)
+    assert torch.equal(toks, ref)
+    assert not (toks[:, S:] == cfg.eos_token_id).any()
+    # an explicit mask takes precedence over pad ids
+    mask = torch.ones(B, S, dtype=torch.long)
+    mask[2, :2] = 0
+    toks2 = m.generate(ids, max_new_tokens=new, min_new_tokens=new, attention_mask=mask)
+    with torch.no_grad():
+        ref2 = opt_ref.greedy_generate(oracle_model(m), ids, new, attention_mask=mask)
+    assert torch.equal(toks2, ref2)
+    # token_latency: (ids, per-token latency list) as greedy_search.py:455-456
+    m.config.token_latency = True
+    out = m.generate(ids, max_new_tokens=new, min_new_tokens=new)
+    assert isinstance(out, tuple) and torch.equal(out[0], toks) and len(out[1]) == new
+
+
+def test_forward_face_prefill_then_decode(cpu_ops):
+    """models.py:371-445: logits [B,1,V] of the last position + the 4-tuple cache whose marker carries the length."""
+    cfg, m = tiny()
+    om = oracle_model(m)
+    B, S, new = 3, 7, 3
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(5))
+    mask = torch.ones(B, S, dtype=torch.long)
+    cache = opt_ref.new_cache(om, B, S + new)
+    logits, past = m(input_ids=ids, attention_mask=mask, prefill_policy=0, decoding_policy=0, num_minibatch=1, max_new_tokens=new)
+    with torch.no_grad():
+        ref = opt_ref.lm_logits(om, opt_ref.decoder_forward(om, ids, mask, cache, 0))
+    assert logits.shape == (B, 1, cfg.vocab_size) and torch.equal(logits, ref)
+    assert len(past) == cfg.num_hidden_layers and past[0][0].shape[2] == S and past[0][1].shape == (S + new, B, 2, 64)
+    cur = torch.argmax(logits[:, -1].float(), dim=-1)[:, None]
+    for t in range(new - 1):
+        mask = torch.cat([mask, mask.new_ones(B, 1)], dim=-1)
+        logits, past = m(input_ids=cur, attention_mask=mask, past_key_values=past, max_new_tokens=new)
+        with torch.no_grad():
+            ref = opt_ref.lm_logits(om, opt_ref.decoder_forward(om, cur, mask, cache, S + t))
+        assert torch.equal(logits, ref), t
+        assert past[0][0].shape[2] == S + t + 1
+        cur = torch.argmax(logits[:, -1].float(), dim=-1)[:, None]
+    with pytest.raises(ValueError):
+        m(input_ids=cur, attention_mask=mask[:, :-1], past_key_values=past)       # M:1127-1131
+    with pytest.raises(NotImplementedError):
+        m(input_ids=ids, prefill_policy=1)                                        # full-CPU policy is not in this build
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_layer_face_vs_reference_goldens(cpu_ops, golden_dir, name):
+    """decoder.py:172-183, 323-335 through OPTDecoderLayer.forward with the reference's 16-entry ``gpu_layer`` list:
+    outputs and cache rows bit-identical to what the reference's own layer code produced (oracle/gen_golden.py)."""
+    meta, w, xs, ys, kc_ref, vc_ref = load_layer_case(golden_dir, name)
+    B, S, h, H, new = (meta[k] for k in ("B", "S", "h", "H", "new"))
+    cfg = lia_b200.OPTConfig(hidden_size=h, num_hidden_layers=1, num_attention_heads=H, ffn_dim=4 * h, vocab_size=64,
+                             max_position_embeddings=64, do_layer_norm_before=meta["pre_ln"])
+    m = lia_b200.OPTForCausalLM(cfg, "cpu")
+    layer = m.model.decoder.layers[0]
+    gpu_layer = [w[k] for k in lia_b200.weights.LAYER_KEYS]
+    past = None
+    for step, (x, y_ref) in enumerate(zip(xs, ys)):
+        out = layer(x, past_key_value=past, use_cache=True, gpu_layer=gpu_layer, policy=0, max_new_tokens=new)
+        y, past = out[0], out[1]
+        assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16)), (name, step)
+        assert past[0].shape[2] == S + step
+        k_new, v_new = out[2], out[3]                                # policy 0 also returns this call's K/V rows (D:331-333)
+        lo = 0 if step == 0 else S + step - 1
+        assert torch.equal(k_new, kc_ref[lo:S + step]) and torch.equal(v_new, vc_ref[lo:S + step])
+    assert torch.equal(past[1][:S + new], kc_ref) and torch.equal(past[2][:S + new], vc_ref)
+
+
+# ------------------------------------------------------------------ opt-350m's shape: post-LN, project_in/out, no final LN
+
+def test_postln_projected_model_generate_matches_oracle(cpu_ops):
+    cfg, m = tiny(do_layer_norm_before=False, word_embed_proj_dim=64)
+    dec = m.model.decoder
+    assert dec.final_ln_w is None and dec.project_in.shape == (128, 64) and dec.project_out.shape == (64, 128)
+    assert dec.embed_tokens.shape == (cfg.vocab_size, 64)
+    B, S, new = 5, 8, 4
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(7))
+    ids[0, :2] = cfg.pad_token_id
+    toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=2)
+    with torch.no_grad():
+        ref = opt_ref.greedy_generate(oracle_model(m), ids, new)
+    assert torch.equal(toks, ref)
+    # launch sequence of one post-LN layer: fused QKV, attention, out_proj(+res), LN, fc1(+relu), fc2(+res), LN
+    seq = [c for c in cpu_ops.log]
+    first_qkv = next(i for i, c in enumerate(seq) if c[0] == "gemm" and c[1] == 3)
+    assert [c[0] for c in seq[first_qkv:first_qkv + 7]] == ["gemm", "attn_prefill", "gemm", "layernorm", "gemm", "gemm", "layernorm"]
+    # embeddings: token rows, position rows, then project_in with the positions as its residual (M:1139-1142)
+    assert [c[0] for c in seq[:3]] == ["embed", "embed", "gemm"] and seq[2][1] == 2 and seq[2][3:] == (128, 64)
+
+
+def test_postln_projected_model_matches_stock_transformers(cpu_ops, golden_dir):
+    """The whole surface on an HF state dict of opt-350m's architecture (tests/golden/model_hf_postln_tiny.npz, made by
+    stock transformers in fp32): same greedy tokens, bf16 logits within the reference's nightly tolerance (0.1)."""
+    z = np.load(os.path.join(golden_dir, "model_hf_postln_tiny.npz"))
+    bf = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(BF16)  # noqa: E731
+    sd = {k[3:]: bf(z[k]) for k in z.files if k.startswith("sd:")}
+    cfg = lia_b200.OPTConfig(hidden_size=int(z["h"]), num_hidden_layers=int(z["L"]), num_attention_heads=int(z["H"]),
+                             ffn_dim=4 * int(z["h"]), vocab_size=int(z["V"]), max_position_embeddings=int(z["P"]),
+                             do_layer_norm_before=bool(int(z["pre_ln"])), word_embed_proj_dim=int(z["word_dim"]))
+    m = lia_b200.OPTForCausalLM(cfg, "cpu").load_state_dict(sd)
+    m.use_cuda_graphs = False
+    ids = torch.from_numpy(z["input_ids"])
+    logits, _ = m(input_ids=ids, attention_mask=torch.ones_like(ids), max_new_tokens=int(z["new"]))
+    assert np.abs(logits[:, -1].float().numpy() - z["prefill_last_logits"]).max() < 0.1
+    toks = m.generate(ids, max_new_tokens=int(z["new"]), min_new_tokens=int(z["new"]))
+    with torch.no_grad():
+        ref = opt_ref.greedy_generate(oracle_model(m), ids, int(z["new"]))
+    assert torch.equal(toks, ref)
+    # bf16 rounding may flip a near-tie against the fp32 golden tokens; the first token of every row is far from one here
+    assert np.array_equal(toks[:, ids.shape[1]].numpy(), z["tokens"][:, ids.shape[1]])
+
+
+def test_mismatched_embeddings_are_refused(cpu_ops):
+    cfg = lia_b200.OPTConfig(hidden_size=128, num_hidden_layers=1, num_attention_heads=2, ffn_dim=512, vocab_size=96,
+                             max_position_embeddings=32, do_layer_norm_before=False, word_embed_proj_dim=64)
+    m = lia_b200.OPTForCausalLM(cfg, "cpu")
+    e = lia_b200.weights.random_embeddings(96, 128, 32, 0, embed_dim=64, final_ln=True)       # a final LN a post-LN model lacks
+    with pytest.raises(ValueError, match="final LayerNorm"):
+        m.model.decoder.load_embeddings(e)
+    e = lia_b200.weights.random_embeddings(96, 128, 32, 0, embed_dim=128, final_ln=False)     # no projections, wrong width
+    with pytest.raises(ValueError, match="project_in"):
+        m.model.decoder.load_embeddings(e)

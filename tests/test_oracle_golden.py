@@ -9,7 +9,7 @@ import torch
 
 from oracle import opt_ref
 
-LAYER_CASES = ["layer_d64", "layer_d128", "layer_ragged"]
+LAYER_CASES = ["layer_d64", "layer_d128", "layer_ragged", "layer_postln"]
 
 
 def _bf16(a):
@@ -20,6 +20,7 @@ def load_layer_case(golden_dir, name):
     z = np.load(os.path.join(golden_dir, name + ".npz"))
     w = {k[2:]: _bf16(z[k]) for k in z.files if k.startswith("w_")}
     meta = {k: int(z[k]) for k in ("B", "S", "h", "H", "new")}
+    meta["pre_ln"] = bool(int(z["pre_ln"])) if "pre_ln" in z.files else True     # False: opt-350m's LayerNorm placement
     xs = [_bf16(z[f"x{i}"]) for i in range(meta["new"] + 1)]
     ys = [_bf16(z[f"y{i}"]) for i in range(meta["new"] + 1)]
     return meta, w, xs, ys, _bf16(z["kcache"]), _bf16(z["vcache"])
@@ -34,22 +35,27 @@ def test_layer_bit_exact_vs_reference(golden_dir, name):
     vc = torch.zeros_like(kc)
     cur = 0
     for x, y_ref in zip(xs, ys):
-        y = opt_ref.layer_forward(x, w, H, kc, vc, cur)
+        y = opt_ref.layer_forward(x, w, H, kc, vc, cur, meta["pre_ln"])
         cur += x.shape[1]
         assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16)), name
     assert torch.equal(kc.view(torch.int16), kc_ref.view(torch.int16))
     assert torch.equal(vc.view(torch.int16), vc_ref.view(torch.int16))
 
 
-def load_hf_case(golden_dir):
-    z = np.load(os.path.join(golden_dir, "model_hf_tiny.npz"))
+HF_CASES = ["model_hf_tiny", "model_hf_postln_tiny"]    # the second: opt-350m's shape (post-LN, project_in/out, no final LN)
+
+
+def load_hf_case(golden_dir, name="model_hf_tiny"):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
     sd = {k[3:]: _bf16(z[k]) for k in z.files if k.startswith("sd:")}
     model = opt_ref.model_from_hf_state_dict(sd, int(z["H"]))
     return z, model
 
 
-def test_model_fp32_matches_stock_transformers(golden_dir):
-    z, model = load_hf_case(golden_dir)
+@pytest.mark.parametrize("name", HF_CASES)
+def test_model_fp32_matches_stock_transformers(golden_dir, name):
+    z, model = load_hf_case(golden_dir, name)
+    assert model["pre_ln"] == bool(int(z["pre_ln"])) and (model["project_in"] is not None) == (int(z["word_dim"]) != int(z["h"]))
     m32 = opt_ref.model_to(model, dtype=torch.float32)
     ids = torch.from_numpy(z["input_ids"])
     logits = []
@@ -58,9 +64,10 @@ def test_model_fp32_matches_stock_transformers(golden_dir):
     np.testing.assert_allclose(logits[0].numpy(), z["prefill_last_logits"], atol=2e-5)
 
 
-def test_model_bf16_within_reference_nightly_tolerance(golden_dir):
+@pytest.mark.parametrize("name", HF_CASES)
+def test_model_bf16_within_reference_nightly_tolerance(golden_dir, name):
     # tests/cpu/test_ipex_optimize_transformers_nightly.py:237 uses prec=0.1 for bf16 vs fp32 logits
-    z, model = load_hf_case(golden_dir)
+    z, model = load_hf_case(golden_dir, name)
     ids = torch.from_numpy(z["input_ids"])
     logits = []
     opt_ref.greedy_generate(model, ids, 1, collect_logits=logits)
