@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--num-minibatch", type=int, default=2)
     ap.add_argument("--gpu-percentage", type=int, default=100)
     ap.add_argument("--layers", type=int, default=0, help="debug: override depth (result is then NOT the headline config)")
+    ap.add_argument("--weights", default="normal", choices=["normal", "dummy"],
+                    help="normal(0, 0.02) init (lia/modeling_opt.py:895-904) or the reference's dummy U[0,1) weights "
+                         "(utils/opt-weight-gen.py:61-62; BASELINE.json configs[4])")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
     return ap.parse_args()
@@ -188,11 +191,12 @@ def _main(args, json_out):
     if args.layers:
         cfg.num_hidden_layers = args.layers
     B, S, new = args.batch_size, args.input_tokens, args.max_new_tokens
-    workload = (f"{cfg.name} bf16 random-init, {'fully HBM-resident' if args.gpu_percentage >= 100 else f'gpu-percentage {args.gpu_percentage}, rest streamed from pinned host'}, "
+    workload = (f"{cfg.name} bf16 {'random-init' if args.weights == 'normal' else 'dummy U[0,1) weights'}, {'fully HBM-resident' if args.gpu_percentage >= 100 else f'gpu-percentage {args.gpu_percentage}, rest streamed from pinned host'}, "
                 f"batch {B}, input {S}, max-new-tokens {new}, num-minibatch {args.num_minibatch}"
                 + (f" [DEBUG depth {args.layers}: not the headline config]" if args.layers else
                    " (BASELINE.json configs[1])" if (args.model, B, S, new, args.gpu_percentage) == ("opt-30b", 64, 256, 32, 100) else
-                   " (BASELINE.json configs[3])" if (args.model, B, S, new) == ("opt-66b", 64, 512, 64) else ""))
+                   " (BASELINE.json configs[3])" if (args.model, B, S, new) == ("opt-66b", 64, 512, 64) else
+                   " (BASELINE.json configs[4])" if (args.model, B, S, new, args.weights) == ("opt-175b", 64, 256, 32, "dummy") else ""))
     config = {"workload": workload, "parallelism": f"tp{world}", "l2": "inputs_exceed_l2 (weights+KV per step >> 126 MB)",
               "cuda_graphs": not args.no_graphs}
 
@@ -218,7 +222,7 @@ def _main(args, json_out):
 
     m = lia_b200.OPTForCausalLM(cfg, dev, tp_rank=rank, tp_world=world)
     m.use_cuda_graphs = not args.no_graphs
-    m.init_weights(seed=0, gpu_percentage=args.gpu_percentage)
+    m.init_weights(seed=0, kind=args.weights, gpu_percentage=args.gpu_percentage)
     g = torch.Generator().manual_seed(1234)
     ids_host = torch.randint(3, cfg.vocab_size, (B, S), generator=g).pin_memory()
     ids_dev = ids_host.to(dev)
