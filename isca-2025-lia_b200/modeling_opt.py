@@ -667,6 +667,8 @@ class OPTForCausalLM:
         num_minibatch = int(num_minibatch or 1)
         B, S = input_ids.shape
         new = int(max_new_tokens)
+        if new < 1:
+            raise ValueError(f"max_new_tokens must be at least 1 (got {max_new_tokens})")
         if S + new > self.config.max_position_embeddings:
             raise ValueError(f"S + max_new_tokens = {S + new} exceeds max_position_embeddings")
         min_new = int(min_new_tokens or 0)

@@ -95,6 +95,27 @@ def test_generate_padded_prompt_and_eos_suppression(cpu_ops):
     assert isinstance(out, tuple) and torch.equal(out[0], toks) and len(out[1]) == new
 
 
+def test_generate_edge_shapes(cpu_ops):
+    """One new token (prefill only), a batch the minibatch count does not divide (M:1178 floors; the remainder forms a
+    last short minibatch), more minibatches than sequences, and the length checks."""
+    cfg, m = tiny()
+    om = oracle_model(m)
+    for B, S, new, nmb in [(2, 5, 1, 1), (5, 6, 3, 2), (1, 4, 2, 4), (7, 3, 2, 3)]:
+        ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(B * 10 + S))
+        toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=nmb)
+        with torch.no_grad():
+            ref = opt_ref.greedy_generate(om, ids, new)
+        assert toks.shape == (B, S + new) and torch.equal(toks, ref), (B, S, new, nmb)
+    with pytest.raises(ValueError, match="max_new_tokens"):
+        m.generate(ids, max_new_tokens=0)
+    with pytest.raises(ValueError, match="max_position_embeddings"):
+        m.generate(ids, max_new_tokens=cfg.max_position_embeddings)
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, max_new_tokens=2, num_beams=4)
+    with pytest.raises(ValueError, match="attention_mask"):
+        m.generate(ids, max_new_tokens=2, attention_mask=torch.ones(B, S + 1, dtype=torch.long))
+
+
 def test_forward_face_prefill_then_decode(cpu_ops):
     """models.py:371-445: logits [B,1,V] of the last position + the 4-tuple cache whose marker carries the length."""
     cfg, m = tiny()
