@@ -39,6 +39,10 @@ class KVSpill:
         self.ready = [self._new_event() for _ in range(self.n_slots)]        # H2D into the slot has landed
         self.computed = [self._new_event() for _ in range(self.n_slots)]     # compute no longer touches the slot
         self.loaded = [None] * self.n_slots          # (spilled-layer index, rows present) per slot
+        # --no-overlap (lia/modeling_opt.py:1173): every spilled layer passes through slot 0 and nothing is fetched
+        # ahead, so a layer's H2D copy starts only when the previous spilled layer's kernels have released the slot --
+        # transfer and compute serialise, which is what the reference's ablation flag measures
+        self.overlap = True
         self.h2d_bytes = 0
         self.d2h_bytes = 0
 
@@ -63,11 +67,18 @@ class KVSpill:
         with torch.cuda.stream(self.stream):
             dst.copy_(src, non_blocking=True)
 
+    def _slot(self, j):
+        return j % self.n_slots if self.overlap else 0
+
     # ---- all copies are issued on self.stream, in order: a layer's store always precedes its next load
     def _prefetch(self, j, rows):
-        slot = j % self.n_slots
+        slot = self._slot(j)
         if self.loaded[slot] == (j, rows):
             return
+        # the slot's previous tenant must be done with it (its release recorded `computed`; a never-recorded event
+        # is a no-op): with overlap the release path has already made the stream wait, without it the tenant changes
+        # on every layer
+        self.stream.wait_event(self.computed[slot])
         if rows > 0:
             self._copy_async(self.slot_k[slot][:rows], self.host_k[j][:rows])
             self._copy_async(self.slot_v[slot][:rows], self.host_v[j][:rows])
@@ -77,12 +88,16 @@ class KVSpill:
 
     def begin(self, pos0):
         """Start of a forward that finds ``pos0`` rows cached: make sure the first slots are in flight."""
+        if not self.overlap:
+            return
         for j in range(self.n_slots):
             self._prefetch(j, pos0)
 
     def acquire(self, j, pos0):
         """(K, V) device views of spilled layer j holding rows [0, pos0), valid on the current stream."""
-        slot = j % self.n_slots
+        slot = self._slot(j)
+        if not self.overlap and self.loaded[slot] != (j, pos0):
+            self.computed[slot].record(self._current_stream())   # the copy starts only after everything enqueued so far
         self._prefetch(j, pos0)
         self._current_stream().wait_event(self.ready[slot])
         return self.slot_k[slot], self.slot_v[slot]
@@ -91,15 +106,15 @@ class KVSpill:
         """Layer j's kernels (which appended rows [pos0, pos0+S)) are enqueued: write those rows back to the
         host copy, then recycle the slot for layer j+2 -- wrapping around into the NEXT forward, which will
         find pos0+S rows."""
-        slot = j % self.n_slots
+        slot = self._slot(j)
         self.computed[slot].record(self._current_stream())
         self.stream.wait_event(self.computed[slot])
         self._copy_async(self.host_k[j][pos0:pos0 + S], self.slot_k[slot][pos0:pos0 + S])
         self._copy_async(self.host_v[j][pos0:pos0 + S], self.slot_v[slot][pos0:pos0 + S])
         self.d2h_bytes += 2 * S * self.row * 2
         self.loaded[slot] = (j, pos0 + S)             # the slot now holds this layer with the new rows
-        if self.n <= self.n_slots:
-            return                                    # every spilled layer owns a slot: nothing to recycle
+        if self.n <= self.n_slots or not self.overlap:
+            return                                    # every spilled layer owns a slot (or no fetching ahead): nothing to recycle
         nxt, rows = j + self.n_slots, pos0
         if nxt >= self.n:                             # first layers of the NEXT forward (odd counts: begin() fetches them)
             nxt, rows = nxt - self.n, pos0 + S

@@ -450,6 +450,14 @@ class OPTDecoder:
             self._row_parallel(ffn, v["fc2_w"], v["fc2_b"], ln, x1, ws, big)                          # decoder.py:302-317
             ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=rows)                               # decoder.py:320-321
 
+    def set_overlap(self, overlap, spill=None):
+        """``--no-overlap`` (M:1173): transfers of streamed layers / spilled K/V are not fetched ahead but serialised
+        with the compute that uses them -- the reference's ablation of its prefetch pipeline.  Results are unchanged."""
+        if self.streamer is not None:
+            self.streamer.overlap = bool(overlap)
+        if spill is not None:
+            spill.overlap = bool(overlap)
+
     def run_layers(self, x, kcs, vcs, B, S, pos0, num_minibatch, ws, spill=None):
         """Layer-major, minibatch-minor loop (lia/modeling_opt.py:1222, 1284) with double-buffered
         weight streaming for non-resident layers and, where ``kcs[li] is None``, double-buffered K/V
@@ -508,6 +516,7 @@ class OPTDecoder:
         if attention_mask is not None:                 # only the learned positions depend on it (M:368-378; A:446-449, A:500)
             am = attention_mask.to(self.device, torch.int64).contiguous()
         x = torch.empty(B * S, cfg.hidden_size, dtype=BF16, device=self.device)
+        self.set_overlap(not no_overlap)                                                                       # M:1173
         self.embed_rows(ids, past_len, am, x.view(B, S, cfg.hidden_size), ws)                                  # M:1107-1142
         self.run_layers(x, kcs, vcs, B, S, past_len, num_minibatch, ws)
         hidden = self.final_rows(x, ws).view(B, S, cfg.embed_dim)                                              # M:1563-1567
@@ -674,6 +683,7 @@ class OPTForCausalLM:
         min_new = int(min_new_tokens or 0)
         st = self._state(B, S, new, num_minibatch)
         st.calls += 1
+        dec.set_overlap(not no_overlap, st.spill)                                        # M:1173
         eos = self.config.eos_token_id
         graphs_ok = self.use_cuda_graphs and dec.streamer is None and st.spill is None
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(new + 1)]

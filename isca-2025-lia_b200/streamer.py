@@ -56,9 +56,16 @@ class LayerStreamer:
         if not self.handle:
             raise _lib.LiaError(f"lia_streamer_create: {_lib.last_error()}")
         self.loaded = [-1] * self.n_slots     # which streamed-layer index each slot holds / is receiving
+        # --no-overlap (lia/modeling_opt.py:1173, load_layer(..., overlap=False)): every streamed layer passes through
+        # slot 0 and nothing is fetched ahead; lia_streamer_prefetch waits for the slot's release, i.e. for the previous
+        # streamed layer's kernels, so copy and compute serialise -- the reference's ablation of its weight prefetch
+        self.overlap = True
+
+    def _slot(self, j):
+        return j % self.n_slots if self.overlap else 0
 
     def _prefetch(self, j):
-        slot = j % self.n_slots
+        slot = self._slot(j)
         if self.loaded[slot] == j:
             return
         check(_lib.load().lia_streamer_prefetch(self.handle, slot, self.host[j].data_ptr(), self.layout.nbytes),
@@ -66,12 +73,18 @@ class LayerStreamer:
         self.loaded[slot] = j
 
     def begin(self):
+        if not self.overlap:
+            return
         for j in range(self.n_slots):
             self._prefetch(j)
 
     def acquire(self, j):
         """Views of streamed layer j, valid on the current stream after this call."""
-        slot = j % self.n_slots
+        slot = self._slot(j)
+        if not self.overlap and self.loaded[slot] != j:
+            # the copy starts only after everything enqueued so far on the compute stream (prefetch waits for the release)
+            check(_lib.load().lia_streamer_release(self.handle, slot, torch.cuda.current_stream().cuda_stream),
+                  "lia_streamer_release")
         self._prefetch(j)
         check(_lib.load().lia_streamer_wait(self.handle, slot, torch.cuda.current_stream().cuda_stream),
               "lia_streamer_wait")
@@ -80,10 +93,10 @@ class LayerStreamer:
     def release(self, j):
         """Layer j's compute has been enqueued: recycle its slot for layer j+2 (wrapping around so
         the next forward finds its first layers already in flight)."""
-        slot = j % self.n_slots
+        slot = self._slot(j)
         check(_lib.load().lia_streamer_release(self.handle, slot, torch.cuda.current_stream().cuda_stream),
               "lia_streamer_release")
-        if self.n > self.n_slots:
+        if self.n > self.n_slots and self.overlap:
             nxt = j + self.n_slots
             if nxt >= self.n:
                 nxt -= self.n                      # first layers of the NEXT forward

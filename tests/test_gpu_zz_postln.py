@@ -116,3 +116,22 @@ def test_postln_projected_model_vs_oracle(lia):
     top2 = lg.topk(2, dim=-1)
     safe = (top2.values[:, 0] - top2.values[:, 1]) > 4 * 2.0 ** -8 * top2.values[:, 0].abs()
     assert torch.equal(toks[0][safe, S], top2.indices[safe, 0])
+
+
+def test_no_overlap_is_a_scheduling_knob(lia):
+    """--no-overlap (lia/modeling_opt.py:1173: the reference's ablation of its prefetch pipeline): streamed layers and
+    spilled K/V go through ONE device slot, nothing is fetched ahead.  Tokens must stay bit-identical, with the flag on,
+    off again, and across repeated generate() calls (the slot bookkeeping survives the switch)."""
+    cfg = lia.modeling_opt.get_config("opt-1.3b")
+    cfg.num_hidden_layers = 5
+    ids = torch.randint(3, cfg.vocab_size, (8, 64), generator=torch.Generator().manual_seed(7))
+    kw = dict(max_new_tokens=6, min_new_tokens=6, prefill_policy=0, decoding_policy=0)
+    ref = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=5).generate(ids, **kw)
+    for pct, kv_res in [(40, None), (0, 2), (100, 1)]:
+        m = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=5, gpu_percentage=pct)
+        m.kv_resident_layers = kv_res
+        for no_overlap in (True, True, False, True, False):
+            tok = m.generate(ids, gpu_percentage=pct, no_overlap=no_overlap, num_minibatch=2, **kw)
+            assert torch.equal(tok, ref), (pct, kv_res, no_overlap)
+        del m
+        torch.cuda.empty_cache()

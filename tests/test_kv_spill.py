@@ -105,12 +105,13 @@ def val(layer, row, kv):
     return float(layer * 9 + row + (0.5 if kv else 0.0))
 
 
-def run_generation(n, S, new, seed, lazy_steps=3, cls=None):
+def run_generation(n, S, new, seed, lazy_steps=3, cls=None, overlap=True):
     """Prefill of S rows then new-1 decode steps over n spilled layers, the way OPTDecoder.run_layers drives
     the spill.  Each layer's "kernel" checks that the slot holds exactly its own history and appends its rows."""
     sim = Sim(seed)
     Tmax, B, Hl, d = S + new, 2, 1, 8
     sp = (cls or SimKVSpill)(sim, n, Tmax, B, Hl, d, "cpu")
+    sp.overlap = overlap
     errors = []
 
     def layer_kernel(j, kc, vc, pos0, rows):
@@ -160,6 +161,44 @@ def test_spill_schedule_under_random_interleavings(n):
         if n % 2 == 0:                                    # (odd counts: one layer keeps its slot and is never re-read)
             assert sp.h2d_bytes >= want, (sp.h2d_bytes, want)
     assert sp.d2h_bytes == 2 * n * (5 + 3) * 2 * sp.row * 2   # exactly the appended rows go back, never the history
+
+
+class SerialCheckSpill(SimKVSpill):
+    """An H2D copy (destination inside a device slot) asserts, when it executes, that the compute stream has nothing it
+    could be running at the same time: its queue is empty or its head is a wait that has not been satisfied yet."""
+
+    def __init__(self, sim, *a):
+        super().__init__(sim, *a)
+        self.slot_storages = {t.untyped_storage().data_ptr() for t in self.slot_k + self.slot_v}
+
+    def _copy_async(self, dst, src):
+        h2d = dst.untyped_storage().data_ptr() in self.slot_storages
+
+        def fn():
+            q = self.compute.q
+            if h2d:
+                assert not q or (q[0][0] == "wait" and q[0][1] not in self.sim.done), "an H2D copy ran alongside a runnable kernel"
+            dst.copy_(src)
+        self.stream.enqueue(fn)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5])
+def test_no_overlap_schedule_is_correct_and_serial(n):
+    """--no-overlap (lia/modeling_opt.py:1173): every spilled layer goes through slot 0, nothing is fetched ahead, and a
+    layer's H2D copy is ordered after every kernel enqueued before its acquire."""
+    for seed in range(12):
+        sp = run_generation(n, S=5, new=4, seed=seed, cls=SerialCheckSpill, overlap=False)
+        assert sp.loaded[0] is not None and all(x is None for x in sp.loaded[1:])      # only slot 0 is ever used
+    per_row = 2 * sp.row * 2
+    if n == 1:
+        assert sp.h2d_bytes == 0                          # the one spilled layer keeps the slot
+    else:                                                 # every layer re-reads its history on every decode step, both passes
+        assert sp.h2d_bytes == 2 * n * sum(5 + t - 1 for t in range(1, 4)) * per_row
+    assert sp.d2h_bytes == 2 * n * (5 + 3) * 2 * sp.row * 2
+    # the check itself has teeth: with overlap the same harness sees copies running ahead of pending kernels
+    with pytest.raises(AssertionError, match="H2D copy ran alongside"):
+        for seed in range(40):
+            run_generation(4, S=5, new=4, seed=seed, cls=SerialCheckSpill, overlap=True)
 
 
 def test_simulator_catches_a_missing_event():
