@@ -3,9 +3,11 @@
 Same flags as examples/cpu/inference/python/llm/run.py:169-215 and
 single_instance/run_generation.py:59-118, same printed summary lines
 (run_generation.py:330-354) -- plus tokens/s and roofline fractions, which the reference
-never prints.  Prompts are synthetic token ids (no tokenizer / prompt.json offline):
-``randint(3, vocab)`` of length --input-tokens, identical for every batch row as in
-run_generation.py:285.
+never prints.  When -m is a checkpoint directory that carries a tokenizer, --prompt (or the
+"opt" pool of a prompt.json next to run.py / in the working directory) is tokenised and the output
+decoded exactly as run_generation.py:260-285, 319 does; otherwise (random-init models, no
+tokenizer offline) prompts are synthetic token ids: ``randint(3, vocab)`` of length --input-tokens,
+identical for every batch row as in run_generation.py:285.
 
 Policy mapping: 0/2/3/4 run everything on the GPU (non-resident layers streamed from pinned
 host memory); 1 (the reference's default: full-CPU IPEX/AMX) is refused with a pointer to
@@ -49,6 +51,50 @@ def build_parser():
     return p
 
 
+def load_tokenizer(model_id):
+    """The tokenizer the reference loads next to the model (run_generation.py:169-171), when the checkpoint directory
+    carries one (tokenizer.json or vocab.json + merges.txt); None otherwise -- then prompts are synthetic token ids."""
+    if not os.path.isdir(model_id):
+        return None
+    names = set(os.listdir(model_id))
+    if not ({"tokenizer.json"} & names or {"vocab.json", "merges.txt"} <= names):
+        return None
+    from transformers import AutoTokenizer
+    return AutoTokenizer.from_pretrained(model_id, local_files_only=True)
+
+
+def pick_prompt(args, search_dirs):
+    """run_generation.py:260-276: --prompt, else the entry of prompt.json's "opt" pool for --input-tokens."""
+    if args.prompt is not None:
+        return args.prompt
+    for d in search_dirs:
+        pj = os.path.join(d, "prompt.json")
+        if os.path.exists(pj):
+            pool = json.load(open(pj)).get("opt", {})
+            if int(args.input_tokens) > 8192 and "8192" in pool:
+                return pool["8192"] * int(int(args.input_tokens) / 8192)
+            if str(args.input_tokens) in pool:
+                return pool[str(args.input_tokens)]
+    return None
+
+
+def build_inputs(args, vocab_size, tokenizer=None, search_dirs=()):
+    """-> (input_ids [B, S] int64 on the host, prompt text or None).  With a tokenizer and a prompt the ids are the
+    tokenizer's (every batch row the same text, run_generation.py:285); otherwise synthetic ids of --input-tokens."""
+    import torch
+    text = pick_prompt(args, search_dirs) if tokenizer is not None else None
+    if tokenizer is not None and text is None and args.prompt is None:
+        print("[WARN] tokenizer found but no --prompt / prompt.json entry for --input-tokens %s: using synthetic token ids"
+              % args.input_tokens, file=sys.stderr)
+    if text is not None:
+        row = tokenizer(text, return_tensors="pt").input_ids                       # [1, S]
+        print("---- Prompt size:", row.size(dim=1))                                # run_generation.py:279
+    else:
+        g = torch.Generator().manual_seed(1234)
+        row = torch.randint(3, vocab_size, (1, int(args.input_tokens)), generator=g)
+    return row.expand(args.batch_size, row.shape[1]).contiguous().to(torch.int64), text
+
+
 def main(argv=None):
     args = build_parser().parse_args(argv)
     print(args)
@@ -88,9 +134,11 @@ def main(argv=None):
         model = lia_b200.OPTForCausalLM(cfg, dev, tp_rank=rank, tp_world=world)
         model.init_weights(seed=args.seed, kind="dummy" if args.dummy_weights else "normal",
                            gpu_percentage=args.gpu_percentage)
-    g = torch.Generator().manual_seed(1234)
-    prompt = torch.randint(3, cfg.vocab_size, (1, S), generator=g)
-    input_ids = prompt.expand(args.batch_size, S).contiguous().pin_memory()       # run_generation.py:285
+    tokenizer = load_tokenizer(args.model_id)
+    here = os.path.dirname(os.path.abspath(__file__))
+    input_ids, text = build_inputs(args, cfg.vocab_size, tokenizer, (os.getcwd(), here, os.path.dirname(here)))
+    input_ids = input_ids.pin_memory()                                            # run_generation.py:285
+    S = input_ids.shape[1]
     generate_kwargs = dict(do_sample=False, temperature=0.9, num_beams=1 if args.greedy else 1,
                            max_new_tokens=args.max_new_tokens, min_new_tokens=args.max_new_tokens,
                            prefill_policy=args.prefill_policy, decoding_policy=args.decoding_policy,
@@ -100,12 +148,18 @@ def main(argv=None):
     num_iter, num_warmup = args.num_iter, args.num_warmup
     for i in range(num_iter):
         tic = time.time()
+        if text is not None:                    # the reference times tokenizer -> generate -> batch_decode (run_generation.py:308-319)
+            input_ids = tokenizer([text] * args.batch_size, return_tensors="pt").input_ids.pin_memory()
         output = model.generate(input_ids, **generate_kwargs)
         gen_ids = output[0] if args.token_latency else output
+        gen_text = tokenizer.batch_decode(gen_ids, skip_special_tokens=True) if text is not None else None   # run_generation.py:319
         toc = time.time()
         total_new_tokens = [int(o.shape[0]) - S for o in gen_ids]
         if rank == 0:
-            print(total_new_tokens[:4], flush=True)
+            if gen_text is not None:
+                print(gen_text[:2], total_new_tokens[:4], flush=True)             # run_generation.py:329
+            else:
+                print(total_new_tokens[:4], flush=True)
             print("Iteration: %d, Time: %.6f sec" % (i, toc - tic), flush=True)
         if i >= num_warmup:
             total_time += toc - tic

@@ -126,6 +126,40 @@ def test_cli_has_every_reference_flag():
     assert main(["-m", "facebook/opt-1.3b"]) == 2                        # default policy 1/1 = CPU path: refused
 
 
+def test_cli_prompt_and_tokenizer_inputs(tmp_path, capsys):
+    """Caller side of the path (run_generation.py:169-171, 260-285, 319): a checkpoint directory that carries a tokenizer
+    turns --prompt / prompt.json text into ids (every batch row the same text) and ids back into text; without one the
+    ids are synthetic.  No GPU involved: only the input builder is exercised."""
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+    from lia_b200.run import build_inputs, build_parser, load_tokenizer, pick_prompt
+    words = ["<pad>", "</s>", "<unk>"] + "the quick brown fox jumps over a lazy dog and keeps running".split()
+    tk = Tokenizer(models.WordLevel({w: i for i, w in enumerate(words)}, unk_token="<unk>"))
+    tk.pre_tokenizer = pre_tokenizers.Whitespace()
+    d = tmp_path / "ckpt"
+    d.mkdir()
+    PreTrainedTokenizerFast(tokenizer_object=tk, pad_token="<pad>", eos_token="</s>", unk_token="<unk>").save_pretrained(str(d))
+    tok = load_tokenizer(str(d))
+    assert tok is not None and load_tokenizer("facebook/opt-30b") is None and load_tokenizer(str(tmp_path)) is None
+    args = build_parser().parse_args(["--batch-size", "3", "--input-tokens", "6", "--prompt", "the quick brown fox"])
+    ids, text = build_inputs(args, 50272, tok)
+    assert text == "the quick brown fox" and ids.shape == (3, 4) and ids.dtype == torch.int64
+    assert torch.equal(ids[0], ids[2]) and ids[0].tolist() == [3, 4, 5, 6]
+    assert "---- Prompt size: 4" in capsys.readouterr().out                       # run_generation.py:279
+    assert tok.batch_decode(ids, skip_special_tokens=True)[1] == "the quick brown fox"
+    # prompt.json pool keyed by model type and --input-tokens (run_generation.py:262-276)
+    json.dump({"opt": {"6": "a lazy dog keeps running and"}}, open(tmp_path / "prompt.json", "w"))
+    args = build_parser().parse_args(["--batch-size", "2", "--input-tokens", "6"])
+    assert pick_prompt(args, [str(tmp_path)]) == "a lazy dog keeps running and"
+    ids, text = build_inputs(args, 50272, tok, [str(tmp_path)])
+    assert ids.shape == (2, 6) and text.startswith("a lazy dog")
+    # no tokenizer (or no prompt for that length): synthetic ids of exactly --input-tokens, seeded, never pad/eos
+    ids, text = build_inputs(args, 50272, None)
+    assert text is None and ids.shape == (2, 6) and int(ids.min()) >= 3 and torch.equal(ids, build_inputs(args, 50272, None)[0])
+    args = build_parser().parse_args(["--input-tokens", "7"])
+    assert build_inputs(args, 50272, tok, [str(tmp_path)])[1] is None
+
+
 def test_bench_reference_arm_contract():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "opt-125m",
                           "--batch-size", "2", "--input-tokens", "16", "--max-new-tokens", "4", "--steps", "1", "--warmup", "0"],
