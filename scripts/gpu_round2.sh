@@ -22,6 +22,10 @@ el "bench done"
 timeout 120 python scripts/ab_2cta.py > gpurun_out/${R}_ab_2cta.log 2>&1; tail -8 gpurun_out/${R}_ab_2cta.log
 timeout 120 python scripts/microbench.py decode > gpurun_out/${R}_microbench_decode.log 2>&1; tail -10 gpurun_out/${R}_microbench_decode.log
 el "microbench done"
+# 3b. teacher-forced token parity statistics (all new x B decisions; calibrates the threshold of a future test)
+timeout 150 python scripts/token_parity_report.py opt-1.3b 3 8 256 32 > gpurun_out/${R}_token_parity_1p3b.json 2> gpurun_out/token_parity.err; tail -c 600 gpurun_out/${R}_token_parity_1p3b.json
+timeout 150 python scripts/token_parity_report.py opt-30b 2 8 64 32 > gpurun_out/${R}_token_parity_30b.json 2>> gpurun_out/token_parity.err; tail -c 600 gpurun_out/${R}_token_parity_30b.json
+el "token parity done"
 # 4. ncu launch list of the SAME bench command at depth 8 (shares only), then full captures of the top kernels
 timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 9000 --csv --log-file gpurun_out/${R}_launches_bench_l8.csv \
   python bench.py --layers 8 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
