@@ -253,7 +253,7 @@ def write_slabs(directory, config, layer_fn, embeddings, tp_world=1):
     """Write the native format.  ``layer_fn(i)`` -> full layer dict (any float dtype, CPU or GPU);
     one layer is alive at a time.  Every rank's shard file is written in the same pass."""
     os.makedirs(directory, exist_ok=True)
-    layout = LayerLayout(config.hidden_size, config.ffn_dim, tp_world)
+    layout = LayerLayout(config.hidden_size, config.ffn_dim, tp_world, heads=config.num_attention_heads)
     files = [open(os.path.join(directory, f"rank{r}.slabs"), "wb") for r in range(tp_world)]
     try:
         for i in range(config.num_hidden_layers):
@@ -298,7 +298,7 @@ class SlabCheckpoint:
         self.meta = m
         self.tp_world = int(m["tp_world"])
         self.config = OPTConfig(name=m.get("name", "opt"), **m["config"])
-        self.layout = LayerLayout(self.config.hidden_size, self.config.ffn_dim, self.tp_world)
+        self.layout = LayerLayout(self.config.hidden_size, self.config.ffn_dim, self.tp_world, heads=self.config.num_attention_heads)
         if self.layout.numel != m["layout"]["numel"] or {k: list(v) for k, v in self.layout.offsets.items()} != m["layout"]["offsets"]:
             raise CheckpointError(f"{directory}: slab layout in the file differs from this build's LayerLayout")
         for r in range(self.tp_world):

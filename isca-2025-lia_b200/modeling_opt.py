@@ -34,7 +34,7 @@ from . import _lib, ops, tp as tp_mod
 from .ops import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV
 from .kv_spill import KVSpill, plan_resident_layers
 from .streamer import HostArena, LayerStreamer
-from .weights import LAYER_KEYS, LayerLayout, layer_from_hf_state_dict, pack_layer, random_embeddings, random_layer
+from .weights import LAYER_KEYS, LayerLayout, fuse_layer, layer_from_hf_state_dict, pack_layer, random_embeddings, random_layer
 
 BF16 = torch.bfloat16
 LN_EPS = 1e-5
@@ -78,6 +78,7 @@ OPT_CONFIGS = {
     "opt-125m": _cfg("opt-125m", 12, 768, 12, 3072),
     "opt-350m": _cfg("opt-350m", 24, 1024, 16, 4096, do_layer_norm_before=False, word_embed_proj_dim=512),
     "opt-1.3b": _cfg("opt-1.3b", 24, 2048, 32, 8192),
+    "opt-2.7b": _cfg("opt-2.7b", 32, 2560, 32, 10240),           # head_dim 80: runs zero-padded to 128 (weights.padded_head_dim)
     "opt-6.7b": _cfg("opt-6.7b", 32, 4096, 32, 16384),
     "opt-13b": _cfg("opt-13b", 40, 5120, 40, 20480),
     "opt-30b": _cfg("opt-30b", 48, 7168, 56, 28672),
@@ -126,7 +127,7 @@ class _Workspace:
             if e_dim != h:
                 shapes += [(m, h, e_dim), (m, e_dim, h)]                   # project_in / project_out
         self.gemm = ops.GemmWorkspace(ops.GemmWorkspace.bytes_for(shapes), device)
-        self.attn = ops.attn_decode_workspace(batch, cfg.num_attention_heads // layout.tp, cfg.head_dim, device)
+        self.attn = ops.attn_decode_workspace(batch, cfg.num_attention_heads // layout.tp, layout.dp, device)
 
 
 class _GenState:
@@ -134,7 +135,7 @@ class _GenState:
 
     def __init__(self, model, B, S, new, num_minibatch):
         cfg, dev = model.config, model.device
-        L, d = cfg.num_hidden_layers, cfg.head_dim
+        L, d = cfg.num_hidden_layers, model.layout.dp        # cached rows are head-padded where head_dim is not 64 / 128
         Hl = cfg.num_attention_heads // model.tp_world
         self.B, self.S, self.new = B, S, new
         self.Tmax = S + new
@@ -223,7 +224,7 @@ class OPTDecoderLayer:
         B, S, h = hidden_states.shape
         views = self._views_from_gpu_layer(gpu_layer) if gpu_layer is not None else dec.layer_views(self.idx)
         past_len = 0 if past_key_value is None else int(past_key_value[0].shape[2])
-        Hl, d = dec.config.num_attention_heads // dec.tp_world, dec.config.head_dim
+        Hl, d = dec.config.num_attention_heads // dec.tp_world, dec.layout.dp
         if S != 1:
             if past_len != 0:
                 raise NotImplementedError("multi-token forward with a non-empty KV cache is not supported")
@@ -251,12 +252,7 @@ class OPTDecoderLayer:
         """16-entry list in the reference's order (lia/modeling_opt.py:272-293) -> fused views."""
         if len(gl) != 16:
             raise ValueError("gpu_layer must have 16 entries (ln1 w/b, q w/b, k w/b, v w/b, out w/b, ln2 w/b, fc1 w/b, fc2 w/b)")
-        w = dict(zip(LAYER_KEYS, gl))
-        return {"ln1_w": w["ln1_w"], "ln1_b": w["ln1_b"],
-                "qkv_w": torch.cat([w["q_w"], w["k_w"], w["v_w"]], 0).contiguous(),
-                "qkv_b": torch.cat([w["q_b"], w["k_b"], w["v_b"]], 0).contiguous(),
-                "o_w": w["o_w"], "o_b": w["o_b"], "ln2_w": w["ln2_w"], "ln2_b": w["ln2_b"],
-                "fc1_w": w["fc1_w"], "fc1_b": w["fc1_b"], "fc2_w": w["fc2_w"], "fc2_b": w["fc2_b"]}
+        return fuse_layer(dict(zip(LAYER_KEYS, gl)), self.decoder.layout)
 
 
 class OPTDecoder:
@@ -265,11 +261,10 @@ class OPTDecoder:
     def __init__(self, config, device, tp_rank=0, tp_world=1):
         self.config, self.device = config, torch.device(device)
         self.tp_rank, self.tp_world = tp_rank, tp_world
-        if config.head_dim not in (64, 128):
-            raise NotImplementedError(f"head_dim {config.head_dim} unsupported (kernels handle 64 and 128)")
         if config.num_attention_heads % tp_world or config.ffn_dim % tp_world:
             raise ValueError("heads and ffn_dim must divide by the tensor-parallel world size")
-        self.layout = LayerLayout(config.hidden_size, config.ffn_dim, tp_world)
+        # head_dim 64 / 128 as they are; other multiples of 8 (opt-2.7b: 80) zero-padded per head (weights.padded_head_dim)
+        self.layout = LayerLayout(config.hidden_size, config.ffn_dim, tp_world, heads=config.num_attention_heads)
         self.layers = [OPTDecoderLayer(self, i) for i in range(config.num_hidden_layers)]
         self.scaling = config.head_dim ** -0.5                      # lia/modeling_opt.py:413
         self.embed_tokens = self.embed_positions = self.final_ln_w = self.final_ln_b = None
@@ -503,7 +498,7 @@ class OPTDecoder:
                 raise NotImplementedError("multi-token forward with a non-empty KV cache is not supported")
             new = max_new_tokens if max_new_tokens is not None else cfg.max_position_embeddings - S
             Hl = cfg.num_attention_heads // self.tp_world
-            kcs = [torch.zeros(S + new, B, Hl, cfg.head_dim, dtype=BF16, device=self.device) for _ in self.layers]
+            kcs = [torch.zeros(S + new, B, Hl, self.layout.dp, dtype=BF16, device=self.device) for _ in self.layers]
             vcs = [torch.zeros_like(k) for k in kcs]
             beam = torch.zeros(S + new, B, dtype=torch.long, device=self.device)
         else:

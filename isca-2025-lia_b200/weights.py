@@ -20,13 +20,33 @@ LAYER_KEYS = ("ln1_w", "ln1_b", "q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w",
               "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")   # gpu_layer index order
 
 
-class LayerLayout:
-    """Element offsets of one (possibly TP-sharded) layer inside its slab."""
+def padded_head_dim(d):
+    """The attention kernels are built for head_dim 64 and 128; any other head_dim that is a multiple of 8 (opt-2.7b: 80)
+    runs on them ZERO-PADDED: q/k/v get zero rows and out_proj zero columns per head, so the padded lanes of q.k, of the
+    cached K/V and of the context are exact zeros and every real value is what the unpadded math gives."""
+    if d < 8 or d % 8 or d > 128:
+        raise NotImplementedError(f"head_dim {d} unsupported: the kernels handle multiples of 8 up to 128 (padded to 64 / 128)")
+    return 64 if d <= 64 else 128
 
-    def __init__(self, h, f, tp_world=1):
+
+class LayerLayout:
+    """Element offsets of one (possibly TP-sharded) layer inside its slab.  ``heads`` (total attention heads) enables
+    head padding for head_dims other than 64 / 128; ``hq`` is then the PADDED local attention width."""
+
+    def __init__(self, h, f, tp_world=1, heads=None):
         assert h % tp_world == 0 and f % tp_world == 0
         self.h, self.f, self.tp = h, f, tp_world
         self.hq, self.fq = h // tp_world, f // tp_world
+        self.heads_local = self.d = self.dp = None
+        if heads is not None:
+            assert h % heads == 0
+            self.d = h // heads
+            self.dp = padded_head_dim(self.d)
+            if heads % tp_world == 0:
+                self.heads_local = heads // tp_world
+                self.hq = self.heads_local * self.dp           # == h // tp_world unless the heads are padded
+            elif self.dp != self.d:
+                raise ValueError(f"{heads} heads of padded head_dim {self.d} do not split over {tp_world} ranks")
         shapes = OrderedDict([
             ("ln1_w", (h,)), ("ln1_b", (h,)),
             ("qkv_w", (3 * self.hq, h)), ("qkv_b", (3 * self.hq,)),
@@ -74,15 +94,43 @@ def shard_layer(w, rank, world):
     return s
 
 
+def _pad_head_rows(w, Hl, d, dp):
+    """[Hl*d, ...] -> [Hl*dp, ...]: zero rows after each head's d rows."""
+    out = w.new_zeros((Hl, dp) + tuple(w.shape[1:]))
+    out[:, :d] = w.reshape((Hl, d) + tuple(w.shape[1:]))
+    return out.reshape((Hl * dp,) + tuple(w.shape[1:]))
+
+
+def _pad_head_cols(w, Hl, d, dp):
+    """[N, Hl*d] -> [N, Hl*dp]: zero columns after each head's d columns."""
+    out = w.new_zeros(w.shape[0], Hl, dp)
+    out[:, :, :d] = w.reshape(w.shape[0], Hl, d)
+    return out.reshape(w.shape[0], Hl * dp)
+
+
+def fuse_layer(s, layout):
+    """This rank's (already sharded) 16-tensor layer dict -> the fused tensors the kernels consume: q|k|v stacked row-wise
+    (one QKV GEMM) and, where ``layout`` pads the heads, zero rows / columns per head (see padded_head_dim)."""
+    q = [s["q_w"], s["k_w"], s["v_w"]]
+    b = [s["q_b"], s["k_b"], s["v_b"]]
+    o = s["o_w"]
+    if layout.dp is not None and layout.dp != layout.d:
+        Hl, d, dp = layout.heads_local, layout.d, layout.dp
+        q = [_pad_head_rows(t, Hl, d, dp) for t in q]
+        b = [_pad_head_rows(t, Hl, d, dp) for t in b]
+        o = _pad_head_cols(o, Hl, d, dp)
+    out = {k: s[k] for k in ("ln1_w", "ln1_b", "o_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")}
+    out["qkv_w"], out["qkv_b"], out["o_w"] = torch.cat(q, dim=0), torch.cat(b, dim=0), o
+    return out
+
+
 def pack_layer(w, layout, rank=0, out=None):
     """Pack a FULL layer dict into this rank's slab (flat bf16 tensor on w's device or ``out``)."""
-    s = shard_layer(w, rank, layout.tp)
-    dev = s["q_w"].device
+    s = fuse_layer(shard_layer(w, rank, layout.tp), layout)
+    dev = s["qkv_w"].device
     slab = out if out is not None else torch.empty(layout.numel, dtype=BF16, device=dev)
     v = layout.views(slab)
-    v["qkv_w"].copy_(torch.cat([s["q_w"], s["k_w"], s["v_w"]], dim=0))
-    v["qkv_b"].copy_(torch.cat([s["q_b"], s["k_b"], s["v_b"]], dim=0))
-    for k in ("ln1_w", "ln1_b", "o_w", "o_b", "ln2_w", "ln2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b"):
+    for k in v:
         v[k].copy_(s[k])
     return slab
 

@@ -135,3 +135,40 @@ def test_no_overlap_is_a_scheduling_knob(lia):
             assert torch.equal(tok, ref), (pct, kv_res, no_overlap)
         del m
         torch.cuda.empty_cache()
+
+
+def test_padded_head_dim_vs_unpadded_oracle(lia):
+    """head_dim 80 (opt-2.7b's) runs on the head_dim-128 kernels with zero-padded heads (weights.padded_head_dim): hidden
+    states against the oracle on the UNPADDED weights, padded lanes of the cache exactly zero, deterministic tokens."""
+    from oracle import opt_ref
+    from lia_b200.weights import random_embeddings, random_layer
+    H, d = 4, 80
+    cfg = lia.OPTConfig(hidden_size=H * d, num_hidden_layers=2, num_attention_heads=H, ffn_dim=4 * H * d, vocab_size=512,
+                        max_position_embeddings=96)
+    m = lia.OPTForCausalLM(cfg, "cuda").init_weights(seed=4, bias_std=0.02, ln_std=0.05)
+    assert (m.layout.d, m.layout.dp, m.layout.hq) == (80, 128, H * 128)
+    e = random_embeddings(cfg.vocab_size, cfg.hidden_size, cfg.max_position_embeddings, 4 * 100003 + 17, "cuda", "normal",
+                          cfg.init_std, 0.05, cfg.pad_token_id)
+    layers = [random_layer(cfg.hidden_size, cfg.ffn_dim, 4 * 100003 + 1000 + i, "cuda", "normal", cfg.init_std, 0.02, 0.05)
+              for i in range(cfg.num_hidden_layers)]
+    om = {"H": H, "layers": layers, **e}
+    assert torch.equal(om["embed_tokens"], m.model.decoder.embed_tokens)
+    B, S, new = 4, 40, 6
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(8))
+    ones = torch.ones(B, S, dtype=torch.long, device="cuda")
+    hidden, past = m.model.decoder(input_ids=ids.cuda(), attention_mask=ones, max_new_tokens=new)
+    nxt = torch.randint(3, cfg.vocab_size, (B, 1), generator=torch.Generator().manual_seed(9))
+    ones1 = torch.ones(B, S + 1, dtype=torch.long, device="cuda")
+    hidden1, past1 = m.model.decoder(input_ids=nxt.cuda(), attention_mask=ones1, past_key_values=past, max_new_tokens=new)
+    with torch.no_grad():
+        cache = opt_ref.new_cache(om, B, S + new)
+        href = opt_ref.decoder_forward(om, ids.cuda(), ones, cache, 0)
+        href1 = opt_ref.decoder_forward(om, nxt.cuda(), ones1, cache, S)
+    assert rel_err(hidden, href) <= 3 * REL_TOL and rel_err(hidden1, href1) <= 3 * REL_TOL      # chained through 2 layers
+    for li in range(cfg.num_hidden_layers):
+        k, v = past1[li][1], past1[li][2]
+        assert k.shape == (S + new, B, H, 128) and not k[..., d:].any() and not v[..., d:].any()
+        assert rel_err(k[:S + 1, ..., :d], cache[li][0][:S + 1]) <= 3 * REL_TOL
+        assert rel_err(v[:S + 1, ..., :d], cache[li][1][:S + 1]) <= 3 * REL_TOL
+    toks = [m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=2).cpu() for _ in range(3)]
+    assert torch.equal(toks[0], toks[1]) and torch.equal(toks[1], toks[2])     # eager, graph capture, graph replay

@@ -221,3 +221,59 @@ def test_mismatched_embeddings_are_refused(cpu_ops):
     e = lia_b200.weights.random_embeddings(96, 128, 32, 0, embed_dim=128, final_ln=False)     # no projections, wrong width
     with pytest.raises(ValueError, match="project_in"):
         m.model.decoder.load_embeddings(e)
+
+
+# ------------------------------------------------------------------ head_dim other than 64 / 128 (opt-2.7b: 80): zero-padded heads
+
+def _unpadded_oracle_model(cfg, seed, bias_std, ln_std):
+    """Oracle dict from the SAME generators init_weights() uses, but unpadded (the product's slabs hold padded heads)."""
+    from lia_b200.weights import random_embeddings, random_layer
+    e = random_embeddings(cfg.vocab_size, cfg.hidden_size, cfg.max_position_embeddings, seed * 100003 + 17, "cpu", "normal",
+                          cfg.init_std, ln_std, cfg.pad_token_id, embed_dim=cfg.embed_dim, final_ln=cfg.do_layer_norm_before)
+    layers = [random_layer(cfg.hidden_size, cfg.ffn_dim, seed * 100003 + 1000 + i, "cpu", "normal", cfg.init_std, bias_std, ln_std)
+              for i in range(cfg.num_hidden_layers)]
+    return {"H": cfg.num_attention_heads, "layers": layers, "pre_ln": cfg.do_layer_norm_before, **e}
+
+
+@pytest.mark.parametrize("d", [80, 32, 96])
+def test_padded_head_dim_matches_unpadded_oracle(cpu_ops, d):
+    H = 4
+    cfg = lia_b200.OPTConfig(hidden_size=H * d, num_hidden_layers=2, num_attention_heads=H, ffn_dim=4 * H * d, vocab_size=384,
+                             max_position_embeddings=64)
+    m = lia_b200.OPTForCausalLM(cfg, "cpu").init_weights(seed=4, bias_std=0.05, ln_std=0.1)
+    m.use_cuda_graphs = False
+    lay = m.layout
+    dp = 64 if d <= 64 else 128
+    assert (lay.d, lay.dp, lay.hq) == (d, dp, H * dp)
+    v = m.model.decoder.resident_views[0]
+    assert v["qkv_w"].shape == (3 * H * dp, H * d) and v["o_w"].shape == (H * d, H * dp)
+    q = v["qkv_w"][:H * dp].view(H, dp, H * d)
+    assert not q[:, d:].any() and not v["qkv_b"].view(3, H, dp)[:, :, d:].any() and not v["o_w"].view(H * d, H, dp)[:, :, d:].any()
+    om = _unpadded_oracle_model(cfg, 4, 0.05, 0.1)
+    assert torch.equal(q[:, :d].reshape(H * d, H * d), om["layers"][0]["q_w"])
+    B, S, new = 3, 9, 4
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(1))
+    ones = torch.ones(B, S, dtype=torch.long)
+    hidden, past = m.model.decoder(input_ids=ids, attention_mask=ones, max_new_tokens=new)
+    cache = opt_ref.new_cache(om, B, S + new)
+    with torch.no_grad():
+        href = opt_ref.decoder_forward(om, ids, ones, cache, 0)
+    # padding only adds exact zeros to every dot product: the values are the unpadded ones up to fp32 summation order
+    err = ((hidden.float() - href.float()).abs().max() / href.float().abs().max()).item()
+    assert err <= 1e-2, err
+    for li in range(cfg.num_hidden_layers):
+        k, kref = past[li][1], cache[li][0]
+        assert k.shape == (S + new, B, H, dp) and not k[..., d:].any() and not past[li][2][..., d:].any()
+        if li == 0:                       # K/V of the first layer: same products, same order -> identical bits
+            assert torch.equal(k[:S, ..., :d], kref[:S])
+    toks = m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=2)
+    with torch.no_grad():
+        lg = []
+        ref = opt_ref.greedy_generate(om, ids, new, collect_logits=lg)
+    l0 = lg[0].clone()
+    l0[:, cfg.eos_token_id] = -float("inf")
+    top2 = l0.topk(2, dim=-1).values
+    safe = (top2[:, 0] - top2[:, 1]) > 8 * 2.0 ** -8 * top2[:, 0].abs()
+    assert torch.equal(toks[safe, S], ref[safe, S])
+    with pytest.raises(NotImplementedError, match="head_dim"):
+        lia_b200.OPTForCausalLM(lia_b200.OPTConfig(hidden_size=4 * 136, num_attention_heads=4, ffn_dim=64), "cpu")
