@@ -1,11 +1,14 @@
-"""opt-350m's variant of the layer on a real B200: LayerNorm AFTER each residual add (decoder.py:250-259, 320-321), no
-final LayerNorm (lia/modeling_opt.py:1001-1006) and bias-free project_in / project_out around a narrower token table
-(lia/modeling_opt.py:988-996, 1139-1140, 1566-1567).  Same kernels as the pre-LN path in a different order (the host
-order is pinned bit-exactly on CPU by tests/test_host_model_cpu.py); this file checks the result on the GPU against the
-golden made from the reference's own layer code and against the oracle run on the same GPU.
+"""GPU checks of the paths added after the round-1 GPU budget was spent -- the only GPU tests that had not yet run on
+hardware when committed, which is why the file is named to run after the others.  Each path re-uses the kernels the
+other GPU files verify, in a new order or layout whose HOST side is pinned bit-exactly on CPU (tests/test_host_model_cpu.py,
+tests/test_kv_spill.py):
 
-(Named to run after the other GPU files: it was added when the round's GPU budget was spent, so it is the one GPU test
-file that had not yet run on hardware when committed.)"""
+  * opt-350m's variant of the layer: LayerNorm AFTER each residual add (decoder.py:250-259, 320-321), no final LayerNorm
+    (lia/modeling_opt.py:1001-1006), bias-free project_in / project_out around a narrower token table
+    (lia/modeling_opt.py:988-996, 1139-1140, 1566-1567) -- against the golden made from the reference's own layer code and
+    against the oracle run on the same GPU;
+  * --no-overlap (lia/modeling_opt.py:1173) as a pure scheduling knob;
+  * head_dim 80 (opt-2.7b) on the head_dim-128 kernels with zero-padded heads, against the oracle on the unpadded weights."""
 import os
 
 import numpy as np
