@@ -277,3 +277,55 @@ def test_padded_head_dim_matches_unpadded_oracle(cpu_ops, d):
     assert torch.equal(toks[safe, S], ref[safe, S])
     with pytest.raises(NotImplementedError, match="head_dim"):
         lia_b200.OPTForCausalLM(lia_b200.OPTConfig(hidden_size=4 * 136, num_attention_heads=4, ffn_dim=64), "cpu")
+
+
+# ------------------------------------------------------------------ bench.py's own arm, dry-run
+
+def test_bench_line_contract_dry_run(cpu_ops, monkeypatch):
+    """bench.py's main body executed on the kernel stand-in (device swapped to CPU, event times faked): no number here
+    means anything, but every key of the driver's JSON contract must be present and well-formed, and the instrumented
+    prefill pass must see exactly the projection GEMMs (4 per layer per minibatch)."""
+    import io
+    import json
+    import types
+
+    class Ev:
+        def __init__(self, enable_timing=False):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def elapsed_time(self, other):
+            return 1.0
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    for old, new in (('torch.device("cuda", local)', 'torch.device("cpu")'), (".pin_memory()", ""),
+                     ("m.use_cuda_graphs = not args.no_graphs", "m.use_cuda_graphs = False")):
+        assert old in src
+        src = src.replace(old, new)
+    mod = types.ModuleType("bench_dry")
+    mod.__dict__["__file__"] = os.path.join(ROOT, "bench.py")
+    exec(compile(src, "bench.py", "exec"), mod.__dict__)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--model", "opt-125m", "--batch-size", "4", "--input-tokens", "80", "--max-new-tokens",
+                                      "4", "--num-minibatch", "2", "--no-cpu-baseline", "--layers", "2", "--steps", "2", "--warmup", "3"])
+    out = io.StringIO()
+    assert mod._main(mod.parse(), out) == 0
+    lines = out.getvalue().strip().splitlines()
+    assert len(lines) == 1                                              # ONE JSON line
+    line = json.loads(lines[0])
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert k in line, k
+    assert line["unit"] == "tokens/s" and line["n_gpus"] == 1 and line["steps"] == 2 and line["warmup"] >= 3
+    assert line["higher_is_better"] is True and line["scaling"] == "strong" and line["vs_baseline"] is None and line["dtype"] == "bf16"
+    assert set(line["e2e"]) == {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["e2e"]["h2d_bytes_per_step"] == 4 * 80 * 8 and line["e2e"]["d2h_bytes_per_step"] == 4 * 84 * 8
+    assert set(line["clocks"]) == {"sm_mhz", "sm_max_mhz", "reasons"}
+    r = line["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert k in r, k
+    assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["launches"] == 4 * 2 * 2       # 4 GEMMs x 2 layers x 2 minibatches
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert line["roofline_decode"]["bound"] == "hbm" and "workload" in line["config"] and "model" not in line["config"]
