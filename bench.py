@@ -164,11 +164,26 @@ def cpu_baseline(args, cfg, steps=1, warmup=0):
         if i >= warmup:
             times.append(t)
     t_layer = sum(times) / len(times)
-    tok_s = (Bs * new) / (t_layer * L)
-    sample = (f"1 of {L} decoder layers of {cfg.name} at batch {Bs} (of {B}), input {S}, {new} new tokens, "
-              f"time extrapolated x{L} layers; embeddings/lm_head excluded; host GEMM probe {tf:.2f} TFLOP/s")
+    # the steps either side of the stack, once per generated token: final LayerNorm, tied lm_head on the last position,
+    # argmax (models.py:423-431, greedy_search.py:395) -- timed on their own and added `new` times
+    V = cfg.vocab_size
+    e = (torch.randn(V, h) * 0.02).to(torch.bfloat16)
+    xh = torch.randn(Bs, h).to(torch.bfloat16)
+    lw, lb = torch.ones(h, dtype=torch.bfloat16), torch.zeros(h, dtype=torch.bfloat16)
+    with torch.inference_mode():
+        th = []
+        for i in range(3):
+            t0 = time.perf_counter()
+            torch.argmax(torch.nn.functional.linear(torch.nn.functional.layer_norm(xh, (h,), lw, lb, 1e-5), e).float(), dim=-1)
+            th.append(time.perf_counter() - t0)
+    t_head = min(th[1:])
+    t_total = t_layer * L + t_head * new
+    tok_s = (Bs * new) / t_total
+    sample = (f"1 of {L} decoder layers of {cfg.name} at batch {Bs} (of {B}), input {S}, {new} new tokens, layer time "
+              f"extrapolated x{L} layers, plus {new} x (final LayerNorm + lm_head + argmax) timed separately "
+              f"({t_head * 1e3:.1f} ms each); embedding lookups excluded; host GEMM probe {tf:.2f} TFLOP/s")
     return {"value": tok_s, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample,
-            "sample_seconds": t_layer}, t_layer
+            "sample_seconds": t_layer, "head_seconds": t_head}, t_total / L
 
 
 def main():
