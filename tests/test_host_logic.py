@@ -54,6 +54,43 @@ def test_slab_pack_and_tp_sharding(world):
     assert torch.allclose(total, full, atol=2e-2, rtol=2e-2)
 
 
+@pytest.mark.parametrize("H,d,world", [(4, 80, 1), (4, 80, 2), (8, 32, 4), (2, 96, 1), (4, 64, 2), (2, 128, 2), (6, 40, 3)])
+def test_head_padding_is_exact_and_invertible(H, d, world):
+    """Zero-padded heads (weights.padded_head_dim): per rank, the padded slab holds exactly the shard's values in the
+    first d lanes of every head and zeros elsewhere, and the padded projections compute the unpadded ones:
+    (x Wq^T + bq) in lanes [:d], exact zeros in the rest; ctx_pad Wo_pad^T == ctx Wo^T."""
+    h, f = H * d, 2 * H * d
+    dp = 64 if d <= 64 else 128
+    w = weights.random_layer(h, f, seed=7, bias_std=0.05, ln_std=0.1)
+    for r in range(world):
+        lay = weights.LayerLayout(h, f, world, heads=H)
+        Hl = H // world
+        assert (lay.d, lay.dp, lay.heads_local, lay.hq) == (d, dp, Hl, Hl * dp)
+        v = lay.views(weights.pack_layer(w, lay, r))
+        ref = opt_ref.shard_layer(w, H, r, world)
+        for i, n in enumerate(("q", "k", "v")):
+            blk = v["qkv_w"][i * lay.hq:(i + 1) * lay.hq].view(Hl, dp, h)
+            assert torch.equal(blk[:, :d].reshape(Hl * d, h), ref[n + "_w"]) and not blk[:, d:].any()
+            bb = v["qkv_b"][i * lay.hq:(i + 1) * lay.hq].view(Hl, dp)
+            assert torch.equal(bb[:, :d].reshape(-1), ref[n + "_b"]) and not bb[:, d:].any()
+        ow = v["o_w"].view(h, Hl, dp)
+        assert torch.equal(ow[:, :, :d].reshape(h, Hl * d), ref["o_w"]) and not ow[:, :, d:].any()
+        x = torch.randn(5, h, dtype=torch.float64)
+        qp = (x @ v["qkv_w"][:lay.hq].double().t() + v["qkv_b"][:lay.hq].double()).view(5, Hl, dp)
+        qr = (x @ ref["q_w"].double().t() + ref["q_b"].double()).view(5, Hl, d)
+        assert torch.equal(qp[..., :d], qr) and not qp[..., d:].any()
+        ctx = torch.randn(5, Hl, d, dtype=torch.float64)
+        ctx_pad = torch.zeros(5, Hl, dp, dtype=torch.float64)
+        ctx_pad[..., :d] = ctx
+        assert torch.allclose(ctx_pad.view(5, -1) @ v["o_w"].double().t(), ctx.view(5, -1) @ ref["o_w"].double().t(), atol=1e-12)
+    if dp == d:                       # no padding: the layout is byte-for-byte the unpadded one
+        assert weights.LayerLayout(h, f, world, heads=H).offsets == weights.LayerLayout(h, f, world).offsets
+    with pytest.raises(NotImplementedError):
+        weights.LayerLayout(4 * 136, 64, 1, heads=4)
+    with pytest.raises(NotImplementedError):
+        weights.LayerLayout(4 * 20, 64, 1, heads=4)
+
+
 def streamk_spans(tiles, k_blocks, grid):
     """Python restatement of Sched<SWAP> in csrc/gemm_sm100.cu."""
     total = tiles * k_blocks
