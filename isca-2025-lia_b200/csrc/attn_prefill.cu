@@ -12,6 +12,8 @@
 //   pass 1: s = bf16(q.k) (bmm output), causal mask, exact row max m and l = sum exp(s - m)
 //   pass 2: p = bf16(exp(s - m) / l)  (softmax(dtype=bf16) output), O += p . v, ctx = bf16(O)
 // The extra QK^T costs 0.5x of a tiny kernel and keeps P bit-compatible with the reference.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -222,6 +224,214 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Variant for S <= 64*NT (NT = 4: S <= 256, the headline prompt length), OPT-IN until it has been A/B-checked on
+// hardware (LIA_ATTN_PREFILL_KEEP=1; scripts/ab_attn_prefill.py): the bf16-rounded scores of pass 1 stay in
+// REGISTERS (two per 32-bit register: 16 query rows x 256 keys per warp = 64 registers per thread), so pass 2 needs
+// neither the second Q.K^T nor the second read of K -- a third of the kernel's MMAs and half of its shared-memory
+// traffic.  The numbers are the same by construction: pass 2 consumes exactly the values score_tile() produced
+// (rounded to bf16, masked to -inf) instead of recomputing them, and m, l, p and O are formed as above.
+template <int D, int NT>
+__global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
+                                                                    const bf16* __restrict__ vc, bf16* __restrict__ out,
+                                                                    int H, int S, int cache_batch, int b0) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int PITCH = D + 8;
+  constexpr int TILE_ELEMS = TILE * PITCH;
+  constexpr int KSTEPS = D / 16;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  bf16* sT = reinterpret_cast<bf16*>(smem_raw);            // [2][TILE][PITCH]: K tiles in pass 1, V tiles in pass 2
+
+  const int qi = gridDim.x - 1 - blockIdx.x;               // heaviest (most keys) tiles first; qi < NT
+  const int hh = blockIdx.y;
+  const int b = blockIdx.z;
+  const int q0 = qi * TILE;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2;
+  const int tq = lane & 3;
+  const int row0 = q0 + warp * 16 + g;
+  const int row1 = row0 + 8;
+  const size_t kv_row_stride = (size_t)cache_batch * H * D;
+  const size_t kv_base = ((size_t)(b0 + b) * H + hh) * D;
+
+  uint32_t qf[KSTEPS][4];
+  {
+    const bf16* q_r0 = q + ((size_t)(b * S + row0) * H + hh) * D;
+    const bf16* q_r1 = q + ((size_t)(b * S + row1) * H + hh) * D;
+#pragma unroll
+    for (int kk = 0; kk < KSTEPS; ++kk) {
+      const int c = kk * 16 + tq * 2;
+      qf[kk][0] = row0 < S ? *reinterpret_cast<const uint32_t*>(q_r0 + c) : 0u;
+      qf[kk][1] = row1 < S ? *reinterpret_cast<const uint32_t*>(q_r1 + c) : 0u;
+      qf[kk][2] = row0 < S ? *reinterpret_cast<const uint32_t*>(q_r0 + c + 8) : 0u;
+      qf[kk][3] = row1 < S ? *reinterpret_cast<const uint32_t*>(q_r1 + c + 8) : 0u;
+    }
+  }
+
+  auto load_tile = [&](int stage, int j, const bf16* src) {
+    constexpr int CPR = D / 8;
+    for (int idx = threadIdx.x; idx < TILE * CPR; idx += THREADS) {
+      const int r = idx / CPR;
+      const int c = idx - r * CPR;
+      const int t = j * TILE + r;
+      bf16* dst = sT + stage * TILE_ELEMS + r * PITCH + c * 8;
+      if (t < S) cp_async16(smem_u32(dst), src + (size_t)t * kv_row_stride + kv_base + c * 8);
+      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+  };
+
+  // ---------------- pass 1: scores (kept, packed bf16x2), row max and sum of exponentials
+  uint32_t sk[NT][8][2];   // sk[j][nt][0] = {s(row0,key), s(row0,key+1)}, [1] = the same for row1
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  load_tile(0, 0, kc);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j <= qi) {                                         // uniform over the CTA
+      if (j < qi) {
+        load_tile((j + 1) & 1, j + 1, kc);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      float s[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      const uint32_t kbase = smem_u32(sT + (j & 1) * TILE_ELEMS);
+#pragma unroll
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t r0, r1, r2, r3;
+          const int krow = np * 16 + (lane >> 4) * 8 + (lane & 7);
+          const int kcol = kk * 16 + ((lane >> 3) & 1) * 8;
+          ldmatrix_x4(kbase + (krow * PITCH + kcol) * 2, r0, r1, r2, r3);
+          mma_bf16(s[2 * np], qf[kk], r0, r1);
+          mma_bf16(s[2 * np + 1], qf[kk], r2, r3);
+        }
+      }
+      float t0 = -INFINITY, t1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const int key = j * TILE + nt * 8 + tq * 2;
+        s[nt][0] = (key <= row0) ? bf16r(s[nt][0]) : -INFINITY;
+        s[nt][1] = (key + 1 <= row0) ? bf16r(s[nt][1]) : -INFINITY;
+        s[nt][2] = (key <= row1) ? bf16r(s[nt][2]) : -INFINITY;
+        s[nt][3] = (key + 1 <= row1) ? bf16r(s[nt][3]) : -INFINITY;
+        sk[j][nt][0] = pack_bf16x2(s[nt][0], s[nt][1]);    // exact: the values are already bf16 (or -inf)
+        sk[j][nt][1] = pack_bf16x2(s[nt][2], s[nt][3]);
+        t0 = fmaxf(t0, fmaxf(s[nt][0], s[nt][1]));
+        t1 = fmaxf(t1, fmaxf(s[nt][2], s[nt][3]));
+      }
+      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
+      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
+      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
+      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
+      const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
+      float a0 = 0.f, a1 = 0.f;
+      if (n0 > -INFINITY) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) a0 += expf(s[nt][0] - n0) + expf(s[nt][1] - n0);
+      }
+      if (n1 > -INFINITY) {
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) a1 += expf(s[nt][2] - n1) + expf(s[nt][3] - n1);
+      }
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      l0 = (m0 > -INFINITY ? l0 * expf(m0 - n0) : 0.f) + a0;
+      l1 = (m1 > -INFINITY ? l1 * expf(m1 - n1) : 0.f) + a1;
+      m0 = n0;
+      m1 = n1;
+      __syncthreads();
+    }
+  }
+  const float mm0 = m0 > -INFINITY ? m0 : 0.f, mm1 = m1 > -INFINITY ? m1 : 0.f;
+  const float ll0 = l0 > 0.f ? l0 : 1.f, ll1 = l1 > 0.f ? l1 : 1.f;
+
+  // ---------------- pass 2: p = bf16(exp(s-m)/l) from the kept scores, O += p.v (V tiles only)
+  float o[D / 8][4];
+#pragma unroll
+  for (int nt = 0; nt < D / 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+  load_tile(0, 0, vc);
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    if (j <= qi) {
+      if (j < qi) {
+        load_tile((j + 1) & 1, j + 1, vc);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+        float a, c;
+        unpack_bf16x2(sk[j][2 * k2][0], a, c);
+        pf[k2][0] = pack_bf16x2(expf(a - mm0) / ll0, expf(c - mm0) / ll0);
+        unpack_bf16x2(sk[j][2 * k2][1], a, c);
+        pf[k2][1] = pack_bf16x2(expf(a - mm1) / ll1, expf(c - mm1) / ll1);
+        unpack_bf16x2(sk[j][2 * k2 + 1][0], a, c);
+        pf[k2][2] = pack_bf16x2(expf(a - mm0) / ll0, expf(c - mm0) / ll0);
+        unpack_bf16x2(sk[j][2 * k2 + 1][1], a, c);
+        pf[k2][3] = pack_bf16x2(expf(a - mm1) / ll1, expf(c - mm1) / ll1);
+      }
+      const uint32_t vbase = smem_u32(sT + (j & 1) * TILE_ELEMS);
+#pragma unroll
+      for (int k2 = 0; k2 < 4; ++k2) {
+#pragma unroll
+        for (int dp = 0; dp < D / 16; ++dp) {
+          uint32_t r0, r1, r2, r3;
+          const int vrow = k2 * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
+          const int vcol = dp * 16 + (lane >> 4) * 8;
+          ldmatrix_x4_trans(vbase + (vrow * PITCH + vcol) * 2, r0, r1, r2, r3);
+          mma_bf16(o[2 * dp], pf[k2], r0, r1);
+          mma_bf16(o[2 * dp + 1], pf[k2], r2, r3);
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  bf16* o_r0 = out + ((size_t)(b * S + row0) * H + hh) * D;
+  bf16* o_r1 = out + ((size_t)(b * S + row1) * H + hh) * D;
+#pragma unroll
+  for (int nt = 0; nt < D / 8; ++nt) {
+    const int c = nt * 8 + tq * 2;
+    if (row0 < S) *reinterpret_cast<uint32_t*>(o_r0 + c) = pack_bf16x2(o[nt][0], o[nt][1]);
+    if (row1 < S) *reinterpret_cast<uint32_t*>(o_r1 + c) = pack_bf16x2(o[nt][2], o[nt][3]);
+  }
+}
+
+constexpr int KEEP_TILES = 4;   // scores of up to 4 x 64 keys stay in registers
+
+bool keep_enabled() {   // read per call (like LIA_GEMM_2CTA) so that one process can A/B the two kernels
+  const char* e = getenv("LIA_ATTN_PREFILL_KEEP");
+  return e != nullptr && atoi(e) != 0;
+}
+
+template <int D>
+int launch_prefill_keep(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
+                        cudaStream_t stream) {
+  constexpr int SMEM = 2 * TILE * (D + 8) * 2;
+  auto kern = attn_prefill_keep_kernel<D, KEEP_TILES>;
+  static bool configured = false;
+  if (!configured) {
+    LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  const dim3 grid((S + TILE - 1) / TILE, H, B);
+  lia_launch(kern, dim3(grid), dim3(THREADS), SMEM, stream, q, kc, vc, out, H, S, cache_batch, b0);
+  LIA_LAUNCH_CHECK();
+  return LIA_OK;
+}
+
 template <int D>
 int launch_prefill(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
                    cudaStream_t stream) {
@@ -252,6 +462,10 @@ extern "C" int lia_attn_prefill_bf16(const void* q, const void* k_cache, const v
   const bf16* kp = reinterpret_cast<const bf16*>(k_cache);
   const bf16* vp = reinterpret_cast<const bf16*>(v_cache);
   bf16* op = reinterpret_cast<bf16*>(out);
+  if (S <= TILE * KEEP_TILES && keep_enabled()) {   // opt-in: scores kept in registers between the two passes
+    if (d == 128) return launch_prefill_keep<128>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+    return launch_prefill_keep<64>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+  }
   if (d == 128) return launch_prefill<128>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
   return launch_prefill<64>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
 }
