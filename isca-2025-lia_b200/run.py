@@ -146,6 +146,19 @@ def main(argv=None):
                            num_minibatch=args.num_minibatch, enable_cxl=args.enable_cxl)      # run_generation.py:179-182
     total_time, total_list = 0.0, []
     num_iter, num_warmup = args.num_iter, args.num_warmup
+    if args.profile:
+        # run_generation.py:220-221, 291-307: five profiled generate() calls (wait 1, warm-up 3, active 1), then the
+        # operator table -- here with the CUDA activity as well, sorted by device time, since the work is on the GPU
+        from torch.profiler import ProfilerActivity, profile, schedule
+
+        def trace_handler(prof):
+            if rank == 0:
+                print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30))
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA], schedule=schedule(wait=1, warmup=3, active=1),
+                     on_trace_ready=trace_handler) as prof:
+            for _ in range(5):
+                model.generate(input_ids, **generate_kwargs)
+                prof.step()
     for i in range(num_iter):
         tic = time.time()
         if text is not None:                    # the reference times tokenizer -> generate -> batch_decode (run_generation.py:308-319)
