@@ -265,6 +265,44 @@ def gen_positions_case(name, seed):
     print("wrote", name, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
 
 
+def gen_tp_shard_case(name, seed):
+    """The reference's OWN tensor-parallel sharder (intel_extension_for_pytorch/transformers/tensor_parallel.py:30-141:
+    TensorParallellLinear.shard_weights_by_head / shard_weights_by_block, lifted at run time) applied to one layer's
+    q/k/v (column split by heads), out_proj (row split by heads), fc1 (column split by 64-blocks) and fc2 (row split by
+    64-blocks, bias / world_size :134) for world sizes 2 and 4; stored per rank."""
+    TP_PATH = os.path.join(REF, "intel_extension_for_pytorch/transformers/tensor_parallel.py")
+    ns = {"torch": torch, "nn": nn}
+    by_head = _lift_class_method(TP_PATH, "TensorParallellLinear", "shard_weights_by_head", dict(ns))
+    by_block = _lift_class_method(TP_PATH, "TensorParallellLinear", "shard_weights_by_block", dict(ns))
+    h, H, f = 64, 4, 256
+    d = h // H
+    w = make_layer_weights(h, f, seed)
+
+    def lin(wt, b):
+        m = nn.Linear(wt.shape[1], wt.shape[0], bias=True, dtype=torch.bfloat16)
+        m.weight = nn.Parameter(wt.clone(), requires_grad=False)
+        m.bias = nn.Parameter(b.clone(), requires_grad=False)
+        return m
+    out = {"h": h, "H": H, "f": f, "seed": seed}
+    for k, v in w.items():
+        out["w_" + k] = bf16_bits(v)
+    for world in (2, 4):
+        for rank in range(world):
+            tag = f"w{world}r{rank}_"
+            for n in ("q", "k", "v"):                                   # shard_mha_weights: column split by heads
+                wt, b = by_head(None, lin(w[n + "_w"], w[n + "_b"]), H, H, d, rank, world, True)
+                out[tag + n + "_w"], out[tag + n + "_b"] = bf16_bits(wt.data), bf16_bits(b.data)
+            wt, _ = by_head(None, lin(w["o_w"], w["o_b"]), H, H, d, rank, world, False)       # row split by heads
+            out[tag + "o_w"] = bf16_bits(wt.data)
+            wt, b, cols = by_block(None, lin(w["fc1_w"], w["fc1_b"]), rank, world, True)      # shard_mlp_weights
+            out[tag + "fc1_w"], out[tag + "fc1_b"] = bf16_bits(wt.data), bf16_bits(b.data)
+            wt, b, cols = by_block(None, lin(w["fc2_w"], w["fc2_b"]), rank, world, False)
+            out[tag + "fc2_w"], out[tag + "fc2_b"] = bf16_bits(wt.data), bf16_bits(b.data)   # bias / world_size
+            out[tag + "cols"] = np.array(cols)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print("wrote", name, "bytes", os.path.getsize(os.path.join(OUT, name + ".npz")))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)                                   # bit-stable CPU reductions
@@ -272,6 +310,7 @@ def main():
     gen_layer_case("layer_d128", B=2, S=5, h=128, H=1, new=2, seed=12)
     gen_layer_case("layer_ragged", B=1, S=1 + 16, h=192, H=3, new=1, seed=13)   # h not a power of two
     gen_positions_case("positions_padded", seed=31)
+    gen_tp_shard_case("tp_shard", seed=41)
     gen_hf_model_case("model_hf_tiny", V=320, h=64, H=1, L=2, P=48, B=3, S=7, new=5, seed=21)
     # opt-350m's shape of model: LayerNorm after the residual adds, no final LayerNorm, project_in / project_out
     gen_layer_case("layer_postln", B=2, S=6, h=128, H=2, new=2, seed=14, pre_ln=False)

@@ -22,7 +22,9 @@ against outputs of the reference's own ``OPTDecoderLayer_forward`` /
 functions against stock ``transformers.OPTForCausalLM`` (``model_hf_tiny.npz``);
 ``positions_from_mask`` / ``prepare_attention_mask`` against the reference's own
 ``OPTLearnedPositionalEmbedding.forward`` and ``_prepare_attention_mask_for_generation``
-run on padded prompts (``positions_padded.npz``).
+run on padded prompts (``positions_padded.npz``); ``shard_layer`` against the reference's own tensor-parallel
+sharder (``tp_shard.npz``); the post-LN branch against the reference's own layer code with
+``do_layer_norm_before=False`` (``layer_postln.npz``) and stock transformers (``model_hf_postln_tiny.npz``).
 The reference holds no golden vectors of its own for this path.
 
 Weight dictionaries use the keys

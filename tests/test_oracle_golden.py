@@ -105,3 +105,40 @@ def test_positions_and_mask_rule_bit_exact_vs_reference(golden_dir):
         rows = opt_ref.embed(model, torch.zeros(B, pos.shape[1], dtype=torch.long), full, past)   # token rows are zero
         assert torch.equal(rows.view(torch.int16), _bf16(z[f"rows{step}"]).view(torch.int16))
         full = torch.cat([full, full.new_ones(B, 1)], dim=-1)
+
+
+def test_tp_sharding_rule_bit_exact_vs_reference_sharder(golden_dir):
+    """tests/golden/tp_shard.npz holds what the reference's own sharder (tensor_parallel.py:30-141, lifted and run by
+    oracle/gen_golden.py) cuts out of one layer for world sizes 2 and 4.  The oracle's restatement and the product's
+    slab packer must cut exactly the same rows / columns; row-parallel biases are the reference's ``bias / world_size``
+    (tensor_parallel.py:134 for fc2; LIA applies the same to out_proj, decoder.py:21)."""
+    import lia_b200  # noqa: F401
+    from lia_b200 import weights
+    z = np.load(os.path.join(golden_dir, "tp_shard.npz"))
+    h, H, f = int(z["h"]), int(z["H"]), int(z["f"])
+    w = {k[2:]: _bf16(z[k]) for k in z.files if k.startswith("w_")}
+    for world in (2, 4):
+        for rank in range(world):
+            tag = f"w{world}r{rank}_"
+            ref = {k[len(tag):]: z[k] for k in z.files if k.startswith(tag)}
+            assert list(ref["cols"]) == [i * (f // world) for i in range(world + 1)]       # equal 64-blocks per rank
+            o = opt_ref.shard_layer(w, H, rank, world)
+            p = weights.shard_layer(w, rank, world)
+            for k in ("q_w", "q_b", "k_w", "k_b", "v_w", "v_b", "o_w", "fc1_w", "fc1_b", "fc2_w"):
+                want = _bf16(ref[k]).view(torch.int16)
+                assert torch.equal(o[k].contiguous().view(torch.int16), want), (world, rank, k)
+                assert torch.equal(p[k].contiguous().view(torch.int16), want), (world, rank, k)
+            # the product pre-divides the row-parallel biases (every rank adds its share before the reduction)
+            want_b = _bf16(ref["fc2_b"]).view(torch.int16)
+            assert torch.equal(p["fc2_b"].view(torch.int16), want_b), (world, rank)
+            assert torch.equal(p["o_b"].view(torch.int16), (w["o_b"].float() / world).to(torch.bfloat16).view(torch.int16))
+            # ... and the packed slab holds exactly these shards
+            lay = weights.LayerLayout(h, f, world, heads=H)
+            v = lay.views(weights.pack_layer(w, lay, rank))
+            hq = h // world
+            v0 = weights.LayerLayout(h, f, world).views(weights.pack_layer(w, weights.LayerLayout(h, f, world), rank))   # unpadded heads
+            assert torch.equal(v0["qkv_w"][hq:2 * hq].view(torch.int16), _bf16(ref["k_w"]).view(torch.int16))
+            assert torch.equal(v0["qkv_b"][2 * hq:].view(torch.int16), _bf16(ref["v_b"]).view(torch.int16))
+            assert torch.equal(v0["o_w"].view(torch.int16), _bf16(ref["o_w"]).view(torch.int16))
+            assert torch.equal(v["fc2_w"].view(torch.int16), _bf16(ref["fc2_w"]).view(torch.int16))
+            assert torch.equal(v["fc2_b"].view(torch.int16), want_b)
