@@ -206,3 +206,75 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "tokens/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["higher_is_better"] is True
+
+
+def test_layer_streamer_call_sequences(monkeypatch):
+    """LayerStreamer's calls into the C ABI (lia_streamer_prefetch / wait / release), recorded against a fake library:
+    the double-buffered schedule (layer j in slot j % 2, layer j+2 prefetched when j is released, wrapping into the next
+    forward) and the --no-overlap schedule (everything through slot 0, the copy ordered after all earlier compute by a
+    release recorded at acquire time, nothing fetched ahead)."""
+    from lia_b200 import _lib, streamer
+
+    class Fake:
+        def __init__(self):
+            self.log = []
+
+        def lia_streamer_create(self, arr, n, nbytes):
+            return 1
+
+        def lia_streamer_prefetch(self, h, slot, ptr, nbytes):
+            self.log.append(("prefetch", slot, ptr))
+            return 0
+
+        def lia_streamer_wait(self, h, slot, stream):
+            self.log.append(("wait", slot))
+            return 0
+
+        def lia_streamer_release(self, h, slot, stream):
+            self.log.append(("release", slot))
+            return 0
+
+        def lia_streamer_destroy(self, h):
+            return 0
+    fake = Fake()
+    monkeypatch.setattr(_lib, "load", lambda: fake)
+
+    class S:
+        cuda_stream = 0
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: S())
+    lay = weights.LayerLayout(64, 128)
+    host = [torch.zeros(lay.numel, dtype=torch.bfloat16) for _ in range(4)]
+    ptr = [t.data_ptr() for t in host]
+    st = streamer.LayerStreamer(lay, host, "cpu")
+
+    def forward():
+        fake.log.clear()
+        st.begin()
+        for j in range(4):
+            st.acquire(j)
+            st.release(j)
+        return list(fake.log)
+
+    first = forward()
+    assert first == [("prefetch", 0, ptr[0]), ("prefetch", 1, ptr[1]),
+                     ("wait", 0), ("release", 0), ("prefetch", 0, ptr[2]),
+                     ("wait", 1), ("release", 1), ("prefetch", 1, ptr[3]),
+                     ("wait", 0), ("release", 0), ("prefetch", 0, ptr[0]),       # wraps into the next forward
+                     ("wait", 1), ("release", 1), ("prefetch", 1, ptr[1])]
+    second = forward()                       # the first two layers are already in flight: no prefetch in begin()
+    assert second == first[2:]
+    st.overlap = False
+    serial = forward()
+    # slot 0 holds layer 0 already (wrap-around prefetch of the previous forward): no copy; every later layer is copied
+    # on demand into slot 0, after a release that orders the copy behind all compute enqueued so far
+    assert serial == [("wait", 0), ("release", 0),
+                      ("release", 0), ("prefetch", 0, ptr[1]), ("wait", 0), ("release", 0),
+                      ("release", 0), ("prefetch", 0, ptr[2]), ("wait", 0), ("release", 0),
+                      ("release", 0), ("prefetch", 0, ptr[3]), ("wait", 0), ("release", 0)]
+    serial2 = forward()                      # slot 0 now holds layer 3: layer 0 is copied again
+    assert serial2[:4] == [("release", 0), ("prefetch", 0, ptr[0]), ("wait", 0), ("release", 0)]
+    assert all(c[1] == 0 for c in serial + serial2)
+    st.overlap = True                        # back to double buffering: both slots are (re)filled as needed
+    again = forward()                        # slot 1 still holds layer 1 from the last double-buffered forward
+    assert again == [("prefetch", 0, ptr[0])] + first[2:]
+    st.close()
