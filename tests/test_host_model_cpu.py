@@ -329,3 +329,148 @@ def test_bench_line_contract_dry_run(cpu_ops, monkeypatch):
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["launches"] == 4 * 2 * 2       # 4 GEMMs x 2 layers x 2 minibatches
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert line["roofline_decode"]["bound"] == "hbm" and "workload" in line["config"] and "model" not in line["config"]
+
+
+# ------------------------------------------------------------------ placement knobs end to end: streamed layers, spilled K/V
+
+class _FakeArena:
+    """Stand-in for streamer.HostArena (pinned host memory needs a CUDA driver)."""
+
+    def __init__(self, numel):
+        self.nbytes = int(numel) * 2
+        self.tensor = torch.zeros(int(numel), dtype=BF16)
+
+    def close(self):
+        self.tensor = None
+
+
+class _FakeStreamerLib:
+    """Executes lia_streamer_prefetch as an immediate copy host slab -> slot, so a slot always holds what the schedule put
+    there LAST: a layer computed from the wrong slot, or from a slot that was recycled too early, changes the tokens."""
+
+    def __init__(self):
+        self.streamers = []
+        self.prefetches = 0
+
+    def lia_streamer_create(self, arr, n, nbytes):
+        return len(self.streamers) + 1
+
+    def _st(self, h):
+        return self.streamers[h - 1]
+
+    def lia_streamer_prefetch(self, h, slot, ptr, nbytes):
+        st = self._st(h)
+        src = next(t for t in st.host if t.data_ptr() == ptr)
+        st.slots[slot].copy_(src)
+        self.prefetches += 1
+        return 0
+
+    def lia_streamer_wait(self, h, slot, stream):
+        return 0
+
+    def lia_streamer_release(self, h, slot, stream):
+        return 0
+
+    def lia_streamer_destroy(self, h):
+        return 0
+
+    def lia_streamer_stats(self, h, b, ms):
+        return 0
+
+
+class _EagerStream:
+    def wait_event(self, ev):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class _NoEvent:
+    def record(self, stream=None):
+        pass
+
+
+@pytest.fixture
+def cpu_placement(cpu_ops, monkeypatch):
+    """On top of the kernel stand-in: pinned arenas, the layer streamer's library calls and the spill's streams/events
+    replaced by eager CPU equivalents, so generate() runs with streamed layers and spilled K/V in the CPU suite."""
+    from lia_b200 import _lib, kv_spill, modeling_opt, streamer
+    real_load = _lib.load
+    fake = _FakeStreamerLib()
+
+    class Lib:
+        def __getattr__(self, name):
+            return getattr(fake, name) if name.startswith("lia_streamer_") else getattr(real_load(), name)
+    monkeypatch.setattr(_lib, "load", lambda: Lib())
+    monkeypatch.setattr(streamer, "HostArena", _FakeArena)
+    monkeypatch.setattr(modeling_opt, "HostArena", _FakeArena)
+    monkeypatch.setattr(kv_spill, "HostArena", _FakeArena)
+    real_init = streamer.LayerStreamer.__init__
+
+    def init(self, layout, host_slabs, device):
+        real_init(self, layout, host_slabs, device)
+        fake.streamers.append(self)
+    monkeypatch.setattr(streamer.LayerStreamer, "__init__", init)
+
+    class S:
+        cuda_stream = 0
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a: S())
+    monkeypatch.setattr(kv_spill.KVSpill, "_new_stream", lambda self: _EagerStream())
+    monkeypatch.setattr(kv_spill.KVSpill, "_new_event", lambda self: _NoEvent())
+    monkeypatch.setattr(kv_spill.KVSpill, "_current_stream", lambda self: _EagerStream())
+    monkeypatch.setattr(kv_spill.KVSpill, "_copy_async", lambda self, dst, src: dst.copy_(src))
+    yield fake
+    for st in fake.streamers:          # their handles are fake: they must never reach the real lia_streamer_destroy
+        st.handle = None
+
+
+@pytest.mark.parametrize("pct,kv_res,nmb,no_overlap", [(40, None, 2, False), (0, None, 1, False), (100, 2, 2, False), (40, 1, 2, False),
+                                                       (0, 0, 1, False), (40, 1, 2, True), (0, 3, 1, True), (20, 4, 3, False)])
+def test_streamed_layers_and_spilled_kv_do_not_change_results(cpu_placement, pct, kv_res, nmb, no_overlap):
+    """gpu_percentage (layers streamed through two device slots), kv_resident_layers (K/V of the last layers spilled to
+    host memory and passed through two device slots), num_minibatch and --no-overlap are placement / scheduling knobs:
+    tokens and the cache handed back through past_key_values must equal the fully resident run's, call after call."""
+    cfg = lia_b200.OPTConfig(hidden_size=128, num_hidden_layers=5, num_attention_heads=2, ffn_dim=256, vocab_size=320,
+                             max_position_embeddings=48)
+    B, S, new = 4, 7, 5
+    ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(3))
+    ref_m = lia_b200.OPTForCausalLM(cfg, "cpu").init_weights(seed=9, bias_std=0.05, ln_std=0.1)
+    ref_m.use_cuda_graphs = False
+    ref = ref_m.generate(ids, max_new_tokens=new, min_new_tokens=new)
+    ref_st = next(iter(ref_m._states.values()))
+    T = S + new - 1
+    m = lia_b200.OPTForCausalLM(cfg, "cpu").init_weights(seed=9, bias_std=0.05, ln_std=0.1, gpu_percentage=pct)
+    m.use_cuda_graphs = False
+    m.kv_resident_layers = kv_res
+    dec = m.model.decoder
+    assert dec.n_resident == (5 if pct >= 100 else int(5 * pct / 100)) and (dec.streamer is None) == (pct >= 100)
+    for rep in range(3):                           # state re-use: wrap-around prefetches of the previous call
+        tok = m.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=nmb, gpu_percentage=pct, no_overlap=no_overlap)
+        assert torch.equal(tok, ref), (rep, pct, kv_res)
+        st = next(iter(m._states.values()))
+        assert st.kv_resident == (5 if kv_res is None else kv_res) and (st.spill is None) == (kv_res is None)
+        for li, p in enumerate(st.past_key_values(T)):
+            assert torch.equal(p[1][:T], ref_st.kc[li][:T]) and torch.equal(p[2][:T], ref_st.vc[li][:T]), (rep, li)
+    if dec.streamer is not None:
+        n_str = 5 - dec.n_resident
+        assert cpu_placement.prefetches >= n_str * new        # every streamed layer crosses the "link" once per forward
+        if no_overlap and n_str > 1:
+            assert dec.streamer.loaded[1:] == [-1] * (dec.streamer.n_slots - 1)      # only slot 0 was ever used
+    with pytest.raises(ValueError, match="gpu_percentage"):
+        m.generate(ids, max_new_tokens=new, gpu_percentage=(pct + 50) % 100 + 1 if pct != 100 else 50)
+
+
+def test_host_layer_pool_aliases_streamed_layers(cpu_placement, monkeypatch):
+    """LIA_HOST_LAYER_POOL (host RAM smaller than the streamed weights): streamed layer j aliases pinned slab j % pool."""
+    monkeypatch.setenv("LIA_HOST_LAYER_POOL", "2")
+    cfg = lia_b200.OPTConfig(hidden_size=128, num_hidden_layers=6, num_attention_heads=2, ffn_dim=256, vocab_size=320,
+                             max_position_embeddings=48)
+    m = lia_b200.OPTForCausalLM(cfg, "cpu").init_weights(seed=9, gpu_percentage=34)      # int(6 * 0.34) = 2 resident
+    dec = m.model.decoder
+    assert dec.n_resident == 2 and dec.host_pool == 2 and len(dec.host_slabs) == 4
+    assert dec.host_slabs[0].data_ptr() == dec.host_slabs[2].data_ptr() and dec.host_slabs[1].data_ptr() == dec.host_slabs[3].data_ptr()
+    assert dec.host_arena.nbytes == 2 * m.layout.nbytes
+    m.use_cuda_graphs = False
+    ids = torch.randint(3, cfg.vocab_size, (2, 5), generator=torch.Generator().manual_seed(3))
+    assert m.generate(ids, max_new_tokens=3, gpu_percentage=34).shape == (2, 8)
