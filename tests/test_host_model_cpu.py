@@ -474,3 +474,47 @@ def test_host_layer_pool_aliases_streamed_layers(cpu_placement, monkeypatch):
     m.use_cuda_graphs = False
     ids = torch.randint(3, cfg.vocab_size, (2, 5), generator=torch.Generator().manual_seed(3))
     assert m.generate(ids, max_new_tokens=3, gpu_percentage=34).shape == (2, 8)
+
+
+@pytest.mark.parametrize("golden", ["model_hf_tiny", "model_hf_postln_tiny"])
+def test_from_pretrained_forms_on_cpu(cpu_placement, golden_dir, tmp_path, golden):
+    """from_pretrained (run_generation.py:159-167) over an HF safetensors directory and over the native slab directory,
+    resident and fully streamed, for the plain model and for opt-350m's shape: same slabs as load_state_dict and the
+    greedy tokens of the oracle on those weights (the goldens' stock-transformers tokens where bf16 does not hit a tie)."""
+    import json
+    from lia_b200 import checkpoint
+    z = np.load(os.path.join(golden_dir, golden + ".npz"))
+    bf = lambda a: torch.from_numpy(a.view(np.int16).copy()).view(BF16)  # noqa: E731
+    sd = {k[3:]: bf(z[k]) for k in z.files if k.startswith("sd:")}
+    h, L, H, V, P, e_dim, pre = (int(z[k]) for k in ("h", "L", "H", "V", "P", "word_dim", "pre_ln"))
+    hf = tmp_path / "hf"
+    hf.mkdir()
+    checkpoint.write_safetensors(str(hf / "model.safetensors"), sd)
+    json.dump({"model_type": "opt", "hidden_size": h, "num_hidden_layers": L, "num_attention_heads": H, "ffn_dim": 4 * h,
+               "vocab_size": V, "max_position_embeddings": P, "word_embed_proj_dim": e_dim, "do_layer_norm_before": bool(pre)},
+              open(hf / "config.json", "w"))
+    checkpoint.convert(str(hf), str(tmp_path / "slabs"))
+    ids = torch.from_numpy(z["input_ids"])
+    new = int(z["new"])
+    cfg = lia_b200.OPTConfig(hidden_size=h, num_hidden_layers=L, num_attention_heads=H, ffn_dim=4 * h, vocab_size=V,
+                             max_position_embeddings=P, do_layer_norm_before=bool(pre), word_embed_proj_dim=0 if e_dim == h else e_dim)
+    base = lia_b200.OPTForCausalLM(cfg, "cpu").load_state_dict(sd)
+    base.use_cuda_graphs = False
+    want = base.generate(ids, max_new_tokens=new, min_new_tokens=new)
+    with torch.no_grad():
+        assert torch.equal(want, opt_ref.greedy_generate(oracle_model(base), ids, new))
+    if golden == "model_hf_tiny":
+        assert np.array_equal(want.numpy(), z["tokens"])
+    for d in ("hf", "slabs"):
+        for pct in (100, 0):
+            m = lia_b200.OPTForCausalLM.from_pretrained(str(tmp_path / d), "cpu", gpu_percentage=pct)
+            m.use_cuda_graphs = False
+            dec = m.model.decoder
+            assert dec.n_resident == (L if pct == 100 else 0)
+            assert m.config.do_layer_norm_before == bool(pre) and m.config.embed_dim == e_dim
+            for i in range(L):
+                got = dec.resident[i] if pct == 100 else dec.host_slabs[i]
+                assert torch.equal(got, base.model.decoder.resident[i]), (d, pct, i)
+            assert torch.equal(m.generate(ids, max_new_tokens=new, min_new_tokens=new, gpu_percentage=pct), want), (d, pct)
+    with pytest.raises(ValueError, match="tensor-parallel world"):
+        lia_b200.OPTForCausalLM.from_pretrained(str(tmp_path / "slabs"), "cpu", tp_rank=0, tp_world=2)
