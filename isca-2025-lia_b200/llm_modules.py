@@ -22,6 +22,7 @@ from . import ops
 from .ops import EPI_BIAS_RELU, EPI_BIAS_RESIDUAL
 
 BF16 = torch.bfloat16
+DEVICE = "cuda"        # where the ops keep their parameters (the CPU suite points this at its kernel stand-in's device)
 
 
 class IPEXCustomOpType(Enum):          # values as llm/modules/utils.py:24-40
@@ -36,8 +37,8 @@ class _LinearFusionCUDA:
     TPP blocking, cf. nn/utils/_weight_prepack.py:19-63)."""
 
     def __init__(self, linear):
-        self.weight = linear.weight.detach().to("cuda", BF16).contiguous()
-        self.bias = None if linear.bias is None else linear.bias.detach().to("cuda", BF16).contiguous()
+        self.weight = linear.weight.detach().to(DEVICE, BF16).contiguous()
+        self.bias = None if linear.bias is None else linear.bias.detach().to(DEVICE, BF16).contiguous()
         n, k = self.weight.shape
         self._ws = {}
 
@@ -69,8 +70,8 @@ class LinearAddCUDA(_LinearFusionCUDA):
 class FastLayerNormCUDA:
     def __init__(self, normalized_shape, eps, weight, bias=None):
         self.normalized_shape, self.eps = normalized_shape, eps
-        self.weight = weight.detach().to("cuda", BF16).contiguous()
-        self.bias = (torch.zeros_like(self.weight) if bias is None else bias.detach().to("cuda", BF16).contiguous())
+        self.weight = weight.detach().to(DEVICE, BF16).contiguous()
+        self.bias = (torch.zeros_like(self.weight) if bias is None else bias.detach().to(DEVICE, BF16).contiguous())
 
     def __call__(self, hidden_states):
         return ops.layernorm(hidden_states.contiguous(), self.weight, self.bias, self.eps)

@@ -90,6 +90,17 @@ def make(calls):
     def qkv_args(q_out, k_cache, v_cache, S, pos0, b0, scale):
         return QkvArgs(q_out, k_cache, v_cache, S, pos0, b0, scale)
 
+    def kv_append(q, k, v, k_cache, v_cache, pos0, b0, scale, q_out=None):
+        calls.log.append(("kv_append", tuple(q.shape), pos0, b0))
+        B, S = q.shape[0], q.shape[1]
+        k_cache[pos0:pos0 + S, b0:b0 + B].copy_(k.permute(1, 0, 2, 3))
+        v_cache[pos0:pos0 + S, b0:b0 + B].copy_(v.permute(1, 0, 2, 3))
+        r = q * scale
+        if q_out is None:
+            return r
+        q_out.copy_(r)
+        return q_out
+
     def _attention(q, k_cache, v_cache, B, S, T, b0, causal):
         _, Bc, H, d = k_cache.shape
         qh = q[:B * S].view(B, S, H, d).transpose(1, 2).contiguous().view(B * H, S, d)
@@ -161,7 +172,7 @@ def make(calls):
     def gemm_allreduce(*a, **k):
         raise AssertionError("the fused NVLink exchange has no CPU stand-in (LIA_TP_FUSED=0 path only)")
 
-    return dict(layernorm=layernorm, gemm=gemm, qkv_args=qkv_args, attn_prefill=attn_prefill, attn_decode=attn_decode,
+    return dict(layernorm=layernorm, gemm=gemm, qkv_args=qkv_args, kv_append=kv_append, attn_prefill=attn_prefill, attn_decode=attn_decode,
                 attn_decode_workspace=attn_decode_workspace, embed=embed, argmax=argmax, residual_add=residual_add,
                 gemm_allreduce=gemm_allreduce, GemmWorkspace=GemmWorkspace)
 

@@ -518,3 +518,51 @@ def test_from_pretrained_forms_on_cpu(cpu_placement, golden_dir, tmp_path, golde
             assert torch.equal(m.generate(ids, max_new_tokens=new, min_new_tokens=new, gpu_percentage=pct), want), (d, pct)
     with pytest.raises(ValueError, match="tensor-parallel world"):
         lia_b200.OPTForCausalLM.from_pretrained(str(tmp_path / "slabs"), "cpu", tp_rank=0, tp_world=2)
+
+
+def test_operator_registry_host_logic(cpu_ops, monkeypatch):
+    """The reference's op-level plugin API (ipex.llm.modules, llm/modules/utils.py:24-93) with this build's table: call
+    signatures, shape handling and the (seq_info, key_cache, value_cache, beam_idx) past of IndirectAccessKVCache, on the
+    kernel stand-in (tests/cpu/test_ipex_llm_module.py:166,200 and tests/cpu/test_masked_mha.py are the reference's own
+    checks of these ops)."""
+    from lia_b200 import llm_modules as lm
+    monkeypatch.setattr(lm, "DEVICE", "cpu")
+    assert set(lm.fusion_modules["cuda"]) == {lm.IPEXCustomOpType.LINEAR_RELU, lm.IPEXCustomOpType.LINEAR_ADD,
+                                              lm.IPEXCustomOpType.FAST_LAYERNORM, lm.IPEXCustomOpType.INDIRECTACCESS_KVCACHE}
+    assert {t.name: t.value for t in lm.IPEXCustomOpType} == {"LINEAR_RELU": 3, "LINEAR_ADD": 6, "FAST_LAYERNORM": 12,
+                                                              "INDIRECTACCESS_KVCACHE": 14}          # utils.py:24-40
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(64, 96).to(BF16)
+    x, y = torch.randn(2, 3, 64).to(BF16), torch.randn(2, 3, 96).to(BF16)
+    with torch.no_grad():
+        want = torch.matmul(x, lin.weight.t()) + lin.bias          # two roundings, as the GPU branch's eager ops (A:393-394)
+        assert torch.equal(lm.LinearRelu(lin)(x), torch.relu(want))
+        assert torch.equal(lm.LinearAdd(lin)(x, y), y + want) and lm.LinearAdd(lin)(x, y).shape == (2, 3, 96)
+        ln = torch.nn.LayerNorm(64).to(BF16)
+        ln.weight.normal_(1, 0.1)
+        ln.bias.normal_(0, 0.1)
+        ref_ln = torch.nn.functional.layer_norm(x, (64,), ln.weight, ln.bias, 1e-5)
+        assert torch.equal(lm.FastLayerNorm(64, 1e-5, ln.weight, ln.bias)(x), ref_ln)
+        assert torch.equal(lm.FastLayerNorm.apply(x, 64, ln.weight, ln.bias, 1e-5), ref_ln)
+    B, S, H, d = 2, 5, 2, 64
+    q, k, v = (torch.randn(B, S, H, d).to(BF16) for _ in range(3))
+    cache = lm.IndirectAccessKVCache(text_max_length=16)
+    out, weights_, past = cache(q, k, v, d ** 0.5, None, None, None)
+
+    def naive(q_, k_, v_, causal):
+        s = (q_.float().permute(0, 2, 1, 3) @ k_.float().permute(0, 2, 3, 1)) / d ** 0.5
+        if causal:
+            s = s.masked_fill(torch.triu(torch.ones(s.shape[-2:], dtype=torch.bool), 1), float("-inf"))
+        return (torch.softmax(s, -1) @ v_.float().permute(0, 2, 1, 3)).permute(0, 2, 1, 3)
+    assert weights_ is None and out.shape == (B, S, H, d) and past[0].shape[2] == S and past[1].shape == (16, B, H, d)
+    assert (out.float() - naive(q, k, v, True)).abs().max() <= 2e-2 * naive(q, k, v, True).abs().max()
+    ks, vs = k, v
+    for step in range(2):
+        q1, k1, v1 = (torch.randn(B, 1, H, d).to(BF16) for _ in range(3))
+        out, _, past = cache(q1, k1, v1, d ** 0.5, past, None, None)
+        ks, vs = torch.cat([ks, k1], 1), torch.cat([vs, v1], 1)
+        ref = naive(q1, ks, vs, False)
+        assert past[0].shape[2] == S + step + 1 and (out.float() - ref).abs().max() <= 2e-2 * ref.abs().max()
+    assert torch.equal(past[1][:S + 2].permute(1, 0, 2, 3), ks) and past[3].shape == (16, B)
+    with pytest.raises(NotImplementedError):
+        cache(q, k, v, d ** 0.5, None, torch.ones(1), None)                 # head_mask
