@@ -22,6 +22,7 @@ el "bench done"
 timeout 120 python scripts/ab_2cta.py > gpurun_out/${R}_ab_2cta.log 2>&1; tail -8 gpurun_out/${R}_ab_2cta.log
 timeout 120 python scripts/microbench.py decode > gpurun_out/${R}_microbench_decode.log 2>&1; tail -10 gpurun_out/${R}_microbench_decode.log
 timeout 90 python scripts/ab_attn_prefill.py > gpurun_out/${R}_ab_attn_prefill.log 2>&1; tail -12 gpurun_out/${R}_ab_attn_prefill.log
+timeout 120 python scripts/long_prompt_probe.py > gpurun_out/${R}_long_prompt_probe.log 2>&1; tail -6 gpurun_out/${R}_long_prompt_probe.log
 el "microbench done"
 # 3b. teacher-forced token parity statistics (all new x B decisions; calibrates the threshold of a future test)
 timeout 150 python scripts/token_parity_report.py opt-1.3b 3 8 256 32 > gpurun_out/${R}_token_parity_1p3b.json 2> gpurun_out/token_parity.err; tail -c 600 gpurun_out/${R}_token_parity_1p3b.json
