@@ -1,7 +1,7 @@
 #!/bin/bash
-# First GPU call of round 2 (1 GPU, ~12 min of box time): everything the round-1 evidence is missing for the kernels
+# First GPU call of round 2 (1 GPU, ~15-20 min of box time): everything the round-1 evidence is missing for the kernels
 # that are the defaults now (CTA-pair prefill GEMM), each step under its own timeout, results in gpurun_out/.
-#   gpurun --timeout 900 -- bash scripts/gpu_round2.sh
+#   gpurun --timeout 1500 -- bash scripts/gpu_round2.sh
 # Afterwards, here:  python scripts/ncu_summarise.py r2     (writes profiles/r2_*)
 R=${1:-r2}
 mkdir -p gpurun_out
