@@ -41,7 +41,18 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int D>
+// Softmax arithmetic.  Default: expf and a true division, as the reference's softmax kernel computes in fp32.  FAST
+// (opt-in, LIA_ATTN_FASTMATH=1, until its parity tests have run on hardware): ex2.approx-based __expf and a multiply by
+// the reciprocal of the row sum -- a few fp32 ulps before the SAME bf16 rounding points, for several times fewer
+// instructions in what is the ALU-bound part of this kernel.
+template <bool FAST>
+__device__ __forceinline__ float exp_(float x) { return FAST ? __expf(x) : expf(x); }
+template <bool FAST>
+__device__ __forceinline__ float prob_(float s, float m, float l, float inv_l) {
+  return FAST ? __expf(s - m) * inv_l : expf(s - m) / l;
+}
+
+template <int D, bool FAST>
 __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
                                                                const bf16* __restrict__ vc, bf16* __restrict__ out,
                                                                int H, int S, int cache_batch, int b0) {
@@ -156,24 +167,25 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
     float a0 = 0.f, a1 = 0.f;
     if (n0 > -INFINITY) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) a0 += expf(s[nt][0] - n0) + expf(s[nt][1] - n0);
+      for (int nt = 0; nt < 8; ++nt) a0 += exp_<FAST>(s[nt][0] - n0) + exp_<FAST>(s[nt][1] - n0);
     }
     if (n1 > -INFINITY) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) a1 += expf(s[nt][2] - n1) + expf(s[nt][3] - n1);
+      for (int nt = 0; nt < 8; ++nt) a1 += exp_<FAST>(s[nt][2] - n1) + exp_<FAST>(s[nt][3] - n1);
     }
     a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
     a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
     a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
     a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-    l0 = (m0 > -INFINITY ? l0 * expf(m0 - n0) : 0.f) + a0;
-    l1 = (m1 > -INFINITY ? l1 * expf(m1 - n1) : 0.f) + a1;
+    l0 = (m0 > -INFINITY ? l0 * exp_<FAST>(m0 - n0) : 0.f) + a0;
+    l1 = (m1 > -INFINITY ? l1 * exp_<FAST>(m1 - n1) : 0.f) + a1;
     m0 = n0;
     m1 = n1;
     __syncthreads();
   }
   const float mm0 = m0 > -INFINITY ? m0 : 0.f, mm1 = m1 > -INFINITY ? m1 : 0.f;
   const float ll0 = l0 > 0.f ? l0 : 1.f, ll1 = l1 > 0.f ? l1 : 1.f;
+  const float il0 = 1.f / ll0, il1 = 1.f / ll1;
 
   // ---------------- pass 2: p = bf16(exp(s-m)/l), O += p.v
   float o[D / 8][4];
@@ -193,10 +205,10 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
     uint32_t pf[4][4];   // P as A-fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int k2 = 0; k2 < 4; ++k2) {
-      pf[k2][0] = pack_bf16x2(expf(s[2 * k2][0] - mm0) / ll0, expf(s[2 * k2][1] - mm0) / ll0);
-      pf[k2][1] = pack_bf16x2(expf(s[2 * k2][2] - mm1) / ll1, expf(s[2 * k2][3] - mm1) / ll1);
-      pf[k2][2] = pack_bf16x2(expf(s[2 * k2 + 1][0] - mm0) / ll0, expf(s[2 * k2 + 1][1] - mm0) / ll0);
-      pf[k2][3] = pack_bf16x2(expf(s[2 * k2 + 1][2] - mm1) / ll1, expf(s[2 * k2 + 1][3] - mm1) / ll1);
+      pf[k2][0] = pack_bf16x2(prob_<FAST>(s[2 * k2][0], mm0, ll0, il0), prob_<FAST>(s[2 * k2][1], mm0, ll0, il0));
+      pf[k2][1] = pack_bf16x2(prob_<FAST>(s[2 * k2][2], mm1, ll1, il1), prob_<FAST>(s[2 * k2][3], mm1, ll1, il1));
+      pf[k2][2] = pack_bf16x2(prob_<FAST>(s[2 * k2 + 1][0], mm0, ll0, il0), prob_<FAST>(s[2 * k2 + 1][1], mm0, ll0, il0));
+      pf[k2][3] = pack_bf16x2(prob_<FAST>(s[2 * k2 + 1][2], mm1, ll1, il1), prob_<FAST>(s[2 * k2 + 1][3], mm1, ll1, il1));
     }
     const uint32_t vbase = smem_u32(sV + (j & 1) * TILE_ELEMS);
 #pragma unroll
@@ -231,7 +243,7 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
 // neither the second Q.K^T nor the second read of K -- a third of the kernel's MMAs and half of its shared-memory
 // traffic.  The numbers are the same by construction: pass 2 consumes exactly the values score_tile() produced
 // (rounded to bf16, masked to -inf) instead of recomputing them, and m, l, p and O are formed as above.
-template <int D, int NT>
+template <int D, int NT, bool FAST>
 __global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
                                                                     const bf16* __restrict__ vc, bf16* __restrict__ out,
                                                                     int H, int S, int cache_batch, int b0) {
@@ -334,18 +346,18 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf1
       float a0 = 0.f, a1 = 0.f;
       if (n0 > -INFINITY) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) a0 += expf(s[nt][0] - n0) + expf(s[nt][1] - n0);
+        for (int nt = 0; nt < 8; ++nt) a0 += exp_<FAST>(s[nt][0] - n0) + exp_<FAST>(s[nt][1] - n0);
       }
       if (n1 > -INFINITY) {
 #pragma unroll
-        for (int nt = 0; nt < 8; ++nt) a1 += expf(s[nt][2] - n1) + expf(s[nt][3] - n1);
+        for (int nt = 0; nt < 8; ++nt) a1 += exp_<FAST>(s[nt][2] - n1) + exp_<FAST>(s[nt][3] - n1);
       }
       a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
       a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
       a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
       a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-      l0 = (m0 > -INFINITY ? l0 * expf(m0 - n0) : 0.f) + a0;
-      l1 = (m1 > -INFINITY ? l1 * expf(m1 - n1) : 0.f) + a1;
+      l0 = (m0 > -INFINITY ? l0 * exp_<FAST>(m0 - n0) : 0.f) + a0;
+      l1 = (m1 > -INFINITY ? l1 * exp_<FAST>(m1 - n1) : 0.f) + a1;
       m0 = n0;
       m1 = n1;
       __syncthreads();
@@ -353,6 +365,7 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf1
   }
   const float mm0 = m0 > -INFINITY ? m0 : 0.f, mm1 = m1 > -INFINITY ? m1 : 0.f;
   const float ll0 = l0 > 0.f ? l0 : 1.f, ll1 = l1 > 0.f ? l1 : 1.f;
+  const float il0 = 1.f / ll0, il1 = 1.f / ll1;
 
   // ---------------- pass 2: p = bf16(exp(s-m)/l) from the kept scores, O += p.v (V tiles only)
   float o[D / 8][4];
@@ -374,13 +387,13 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf1
       for (int k2 = 0; k2 < 4; ++k2) {
         float a, c;
         unpack_bf16x2(sk[j][2 * k2][0], a, c);
-        pf[k2][0] = pack_bf16x2(expf(a - mm0) / ll0, expf(c - mm0) / ll0);
+        pf[k2][0] = pack_bf16x2(prob_<FAST>(a, mm0, ll0, il0), prob_<FAST>(c, mm0, ll0, il0));
         unpack_bf16x2(sk[j][2 * k2][1], a, c);
-        pf[k2][1] = pack_bf16x2(expf(a - mm1) / ll1, expf(c - mm1) / ll1);
+        pf[k2][1] = pack_bf16x2(prob_<FAST>(a, mm1, ll1, il1), prob_<FAST>(c, mm1, ll1, il1));
         unpack_bf16x2(sk[j][2 * k2 + 1][0], a, c);
-        pf[k2][2] = pack_bf16x2(expf(a - mm0) / ll0, expf(c - mm0) / ll0);
+        pf[k2][2] = pack_bf16x2(prob_<FAST>(a, mm0, ll0, il0), prob_<FAST>(c, mm0, ll0, il0));
         unpack_bf16x2(sk[j][2 * k2 + 1][1], a, c);
-        pf[k2][3] = pack_bf16x2(expf(a - mm1) / ll1, expf(c - mm1) / ll1);
+        pf[k2][3] = pack_bf16x2(prob_<FAST>(a, mm1, ll1, il1), prob_<FAST>(c, mm1, ll1, il1));
       }
       const uint32_t vbase = smem_u32(sT + (j & 1) * TILE_ELEMS);
 #pragma unroll
@@ -411,16 +424,21 @@ __global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf1
 
 constexpr int KEEP_TILES = 4;   // scores of up to 4 x 64 keys stay in registers
 
+bool fastmath_enabled() {   // read per call so that one process can A/B
+  const char* e = getenv("LIA_ATTN_FASTMATH");
+  return e != nullptr && atoi(e) != 0;
+}
+
 bool keep_enabled() {   // read per call (like LIA_GEMM_2CTA) so that one process can A/B the two kernels
   const char* e = getenv("LIA_ATTN_PREFILL_KEEP");
   return e != nullptr && atoi(e) != 0;
 }
 
-template <int D>
+template <int D, bool FAST>
 int launch_prefill_keep(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
                         cudaStream_t stream) {
   constexpr int SMEM = 2 * TILE * (D + 8) * 2;
-  auto kern = attn_prefill_keep_kernel<D, KEEP_TILES>;
+  auto kern = attn_prefill_keep_kernel<D, KEEP_TILES, FAST>;
   static bool configured = false;
   if (!configured) {
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -432,11 +450,11 @@ int launch_prefill_keep(const bf16* q, const bf16* kc, const bf16* vc, bf16* out
   return LIA_OK;
 }
 
-template <int D>
+template <int D, bool FAST>
 int launch_prefill(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
                    cudaStream_t stream) {
   constexpr int SMEM = 2 * 2 * TILE * (D + 8) * 2;
-  auto kern = attn_prefill_kernel<D>;
+  auto kern = attn_prefill_kernel<D, FAST>;
   static bool configured = false;
   if (!configured) {
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -462,10 +480,15 @@ extern "C" int lia_attn_prefill_bf16(const void* q, const void* k_cache, const v
   const bf16* kp = reinterpret_cast<const bf16*>(k_cache);
   const bf16* vp = reinterpret_cast<const bf16*>(v_cache);
   bf16* op = reinterpret_cast<bf16*>(out);
+  const bool fast = fastmath_enabled();
   if (S <= TILE * KEEP_TILES && keep_enabled()) {   // opt-in: scores kept in registers between the two passes
-    if (d == 128) return launch_prefill_keep<128>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
-    return launch_prefill_keep<64>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+    if (d == 128) return fast ? launch_prefill_keep<128, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
+                              : launch_prefill_keep<128, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+    return fast ? launch_prefill_keep<64, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
+                : launch_prefill_keep<64, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
   }
-  if (d == 128) return launch_prefill<128>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
-  return launch_prefill<64>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+  if (d == 128) return fast ? launch_prefill<128, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
+                            : launch_prefill<128, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+  return fast ? launch_prefill<64, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
+              : launch_prefill<64, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
 }
