@@ -305,6 +305,7 @@ def _main(args, json_out):
             traffic, traffic_note = committed_traffic(os.environ.get("LIA_GEMM_2CTA", "1") != "0")
         roof = {"kernel": "lia_gemm_tcgen05_kernel (prefill projections)", "bound": "tensor", "achieved": ach,
                 "peak": pk["bf16_sustained"], "unit": "TFLOP/s", "frac": ach / pk["bf16_sustained"], "traffic": traffic,
+                "frac_of_burst_peak": ach / pk["bf16_burst"],
                 "launches": len(big), "avg_launch_ms": ms / len(big), "flops_per_launch": flops / len(big),
                 "peak_source": pk["source"] + ", sustained figure (kernel timed inside a long step); burst "
                 + f"{pk['bf16_burst']}", "share_of_step": (ms / 1e3) / (sec / args.steps),
