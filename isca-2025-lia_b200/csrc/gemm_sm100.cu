@@ -505,8 +505,11 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         const __grid_constant__ EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
                         int* __restrict__ flags, unsigned long long* __restrict__ trace) {
-  static_assert(!PAIR || (!SWAP && !TP && BN == 256), "CTA pairs: plain prefill projections with 256-wide tiles only");
+  static_assert(!PAIR || (!SWAP && !TP && (BN == 256 || BN == 224)), "CTA pairs: plain prefill projections with 256/224-wide tiles only");
   using L = SmemLayout<SWAP, BN, STAGES, PAIR>;
+  // TMEM columns from one accumulator to the other: BN, rounded up to the epilogue's 64-column step for tile widths that
+  // are not a multiple of it (BN = 224, the opt-in tile that trims the wave tail of the N = 7168 projections)
+  constexpr int ACC_COLS = (SWAP || BN % 64 == 0) ? BN : ((BN + 63) / 64) * 64;
   // PAIR: rank in the 2-CTA cluster; rank 0 (the "leader") issues every MMA and owns the full / tempty barriers
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
@@ -629,7 +632,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       while (sched.next(w)) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kb = w.kb0; kb < w.kb1; ++kb) {
           mbar_wait(full_bar(stage), phase);
           if (first_full) {
@@ -704,7 +707,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const bf16* rbase = tp.recv(tp.rank, parity) + (size_t)(u / tp.world) * tp.world * (TILE_A * BN);
       constexpr int CPR = BN / 8;             // 16-byte chunks per tile row
       constexpr int CH = 8;                   // chunks per thread in flight: (1 + world) x 8 independent 16-byte loads
-      static_assert(SWAP || (TILE_A * CPR) % (128 * CH) == 0, "tile must split into whole batches");
+      static_assert(SWAP || !TP || (TILE_A * CPR) % (128 * CH) == 0, "tile must split into whole batches");
 #pragma unroll 1
       for (int c0 = et; c0 < TILE_A * CPR; c0 += 128 * CH) {
         float sum[CH][8];
@@ -780,7 +783,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       mbar_wait(tfull_bar(acc), acc_phase);
       if (et == 0) stamp(trace, 5);
       tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(ew * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * ACC_COLS) + ((uint32_t)(ew * 32) << 16);
 
       if (!SWAP) {
         // tile rows = tokens (TMEM lanes), columns = output features
@@ -789,6 +792,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         for (int c0 = 0; c0 < BN; c0 += 64) {
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            if (BN % 64 != 0 && c0 + half * 32 >= BN) continue;   // (compile-time false for 128/256-wide tiles)
             uint32_t v[32];
             tmem_ld32(taddr + c0 + half * 32, v);
             tmem_ld_wait();
@@ -823,7 +827,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "r"(addr));
             const int m = (w.ta * row_tile + (int)cta_rank) * TILE_A + ew * 32 + r;
             const int n = w.tb * BN + c0 + ch * 8;
-            if (m < p.M && n < p.N) {
+            if (m < p.M && n < p.N && (BN % 64 == 0 || c0 + ch * 8 < BN)) {
               float f[8];
               unpack8(q, f);
               if (tp_on) {
@@ -1185,6 +1189,11 @@ bool pair_enabled() {
   return env == nullptr || atoi(env) != 0;
 }
 
+bool bn224_enabled() {
+  const char* env = getenv("LIA_GEMM_BN224");
+  return env != nullptr && atoi(env) != 0;
+}
+
 Plan make_plan(int M, int N, int K, bool allow_pair = false) {
   Plan pl;
   pl.pair = false;
@@ -1210,6 +1219,14 @@ Plan make_plan(int M, int N, int K, bool allow_pair = false) {
     pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
     pl.pair = allow_pair && pl.bn == 256 && M >= 4 * TILE_A && sms >= 2 && pair_enabled();
     pl.tiles_a = pl.pair ? (M + 2 * TILE_A - 1) / (2 * TILE_A) : (M + TILE_A - 1) / TILE_A;
+    if (pl.pair && N % 224 == 0 && bn224_enabled()) {
+      // opt-in (LIA_GEMM_BN224=1, until A/B-checked on hardware): 256 x 224 tiles where they shorten the schedule.
+      // N = 7168, M = 8192 on 74 CTA pairs: 896 tiles of 256 = 12.1 waves -> 13 x 256 columns of work per pair;
+      // 1024 tiles of 224 = 13.8 waves -> 14 x 224 = 5.8 % less.  Same K order per element: bit-identical results.
+      const long long pairs = sms / 2;
+      const long long u256 = (long long)pl.tiles_a * ((N + 255) / 256), u224 = (long long)pl.tiles_a * (N / 224);
+      if (((u224 + pairs - 1) / pairs) * 224 < ((u256 + pairs - 1) / pairs) * 256) pl.bn = 224;
+    }
     pl.tiles_b = (N + pl.bn - 1) / pl.bn;
     const int units = pl.tiles_a * pl.tiles_b;
     if (pl.pair) pl.grid = 2 * (units < sms / 2 ? units : sms / 2);
@@ -1248,8 +1265,9 @@ unsigned long long* trace_buffer() {
 }
 
 // CTA-pair launch: clusters of two CTAs (one TPC) + programmatic dependent launch
+template <int BN>
 int launch_pair(const Plan& pl, const CUtensorMap& tmA, const CUtensorMap& tmB, const EpiParams& ep, cudaStream_t stream) {
-  constexpr int BN = 256, STAGES = 6;
+  constexpr int STAGES = 6;
   using L = SmemLayout<false, BN, STAGES, true>;
   static_assert(L::TOTAL <= 232448, "shared memory budget exceeded");
   auto kern = lia_gemm_tcgen05_kernel<false, BN, STAGES, false, true>;
@@ -1433,7 +1451,7 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
   } else {
     if ((rc = make_tmap(&tmA, A, M, K, TILE_A)) != LIA_OK) return rc;
     if ((rc = make_tmap(&tmB, W, N, K, pl.pair ? pl.bn / 2 : pl.bn)) != LIA_OK) return rc;
-    if (pl.pair) return launch_pair(pl, tmA, tmB, ep, stream);
+    if (pl.pair) return pl.bn == 224 ? launch_pair<224>(pl, tmA, tmB, ep, stream) : launch_pair<256>(pl, tmA, tmB, ep, stream);
     if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, flags, stream);
   }

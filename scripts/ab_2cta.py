@@ -29,9 +29,16 @@ for label, N, K, epi in [("qkv", 3 * h, h, 0), ("out", h, h, 2), ("fc1", f, h, 1
     bias = torch.randn(N, device=dev).to(torch.bfloat16)
     res = torch.randn(M, N, device=dev).to(torch.bfloat16) if epi == 2 else None
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    for flag in ("0", "1"):
-        os.environ["LIA_GEMM_2CTA"] = flag
+    outs = {}
+    for flag, bn224 in (("0", "0"), ("1", "0"), ("1", "1")):
+        # LIA_GEMM_BN224=1 (opt-in): 256 x 224 pair tiles where they shorten the schedule (N = 7168: 13.8 waves of 224
+        # instead of 12.1 -> 13 waves of 256); same K order per element, so the output must be bit-identical
+        os.environ["LIA_GEMM_2CTA"], os.environ["LIA_GEMM_BN224"] = flag, bn224
         ms = timeit(lambda i: ops.gemm(a, ws_[i % 2], bias, out=out, epilogue=epi, residual=res))
-        print(f"{label:4s} M={M} N={N:6d} K={K:6d} 2cta={flag}: {ms * 1e3:9.1f} us  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s", flush=True)
+        outs[(flag, bn224)] = ops.gemm(a, ws_[0], bias, epilogue=epi, residual=res)
+        torch.cuda.synchronize()
+        same = "" if (flag, bn224) == ("0", "0") else f"  bit-identical to one-CTA: {bool(torch.equal(outs[(flag, bn224)], outs[('0', '0')]))}"
+        print(f"{label:4s} M={M} N={N:6d} K={K:6d} 2cta={flag} bn224={bn224}: {ms * 1e3:9.1f} us  {2.0 * M * N * K / ms / 1e9:8.1f} TFLOP/s{same}", flush=True)
+    outs.clear()
     del ws_, a, out, res
     torch.cuda.empty_cache()

@@ -12,8 +12,8 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 timeout 420 python -m pytest tests -m gpu -x -q --durations=10 > gpurun_out/pytest_gpu.log 2>&1
 echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
 el "pytest done"; tail -16 gpurun_out/pytest_gpu.log
-# 1b. opt-in kernel variants (prefill attention: keep-scores, fast-math): parity only when asked for
-LIA_TEST_OPTIN=1 timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -q -k optin > gpurun_out/pytest_optin.log 2>&1
+# 1b. opt-in kernel variants (prefill attention: keep-scores, fast-math; 256x224 pair GEMM tiles): parity only when asked for
+LIA_TEST_OPTIN=1 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_gemm_2cta.py -m gpu -q -k "optin or bn224" > gpurun_out/pytest_optin.log 2>&1
 echo "pytest optin exit $?" >> gpurun_out/pytest_optin.log; tail -6 gpurun_out/pytest_optin.log
 # 2. headline bench, default kernels (CTA pair), then the one-CTA prefill kernel for the A/B on the whole step
 timeout 200 python bench.py --steps 3 --warmup 3 > gpurun_out/${R}_bench_n1.json 2> gpurun_out/bench_n1.err
