@@ -116,7 +116,9 @@ int lia_kv_append_bf16(const void* q, const void* k, const void* v, void* q_out,
                        int S, int hq, int pos0, int cache_batch, int b0, float q_scale, lia_stream_t stream);
 
 /* hidden[b,s,:] = embed_tokens[ids[b,s]] + embed_positions[past_len + s + 2]  (M:1107-1142 with
- * an all-ones attention mask, M:368-378).  ids int64 [B,S]. */
+ * an all-ones attention mask, M:368-378).  ids int64 [B,S].  Either table (not both) may be NULL: its rows
+ * then contribute nothing and the other table's rows are copied through -- opt-350m's project_in path looks
+ * token rows [word_embed_proj_dim] and position rows [hidden] up separately (M:1139-1142). */
 int lia_embed_bf16(const int64_t* ids, const void* embed_tokens, const void* embed_positions, void* out, int B,
                    int S, int h, int past_len, int vocab, int max_pos_rows, lia_stream_t stream);
 

@@ -12,7 +12,19 @@
 
 #include "common.cuh"
 
+// Allocation and release may be entered while SOME stream of the process is capturing a CUDA graph (a Python finalizer
+// fired by the garbage collector in the middle of a capture; a second model built while the first one's decode graphs
+// are being captured).  Under the default global capture mode such "potentially unsafe" calls (cudaFree, cudaFreeHost,
+// cudaMalloc, stream/event destruction) would INVALIDATE that capture; switching this thread to relaxed mode for the
+// duration of the call is the runtime's own mechanism for allocators (cudaThreadExchangeStreamCaptureMode).
+struct RelaxedCaptureMode {
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+  ~RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
 extern "C" void* lia_host_arena_alloc(size_t bytes) {
+  RelaxedCaptureMode relaxed;
   void* p = nullptr;
   if (bytes == 0) {
     lia_set_error("lia_host_arena_alloc: zero bytes");
@@ -29,6 +41,7 @@ extern "C" void* lia_host_arena_alloc(size_t bytes) {
 
 extern "C" int lia_host_arena_free(void* ptr, size_t /*bytes*/) {
   if (ptr == nullptr) return LIA_OK;
+  RelaxedCaptureMode relaxed;
   LIA_CUDA(cudaFreeHost(ptr));
   return LIA_OK;
 }
@@ -40,9 +53,21 @@ struct LiaStreamer {
   std::vector<cudaEvent_t> ready;     // copy into slot finished
   std::vector<cudaEvent_t> released;  // compute no longer reads slot
   std::vector<bool> has_release;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing;
+  // copy timing: a fixed ring of event pairs, re-used and folded into copy_ms when recycled -- nothing is created on
+  // the hot path and nothing accumulates when the caller never asks for statistics
+  static constexpr int TIMING_RING = 64;
+  cudaEvent_t t0[TIMING_RING] = {};
+  cudaEvent_t t1[TIMING_RING] = {};
+  bool pending[TIMING_RING] = {};
+  int ring_pos = 0;
   double bytes = 0.0;
   double copy_ms = 0.0;
+  void fold(int i) {
+    if (!pending[i]) return;
+    float ms = 0.f;
+    if (cudaEventSynchronize(t1[i]) == cudaSuccess && cudaEventElapsedTime(&ms, t0[i], t1[i]) == cudaSuccess) copy_ms += ms;
+    pending[i] = false;
+  }
 };
 
 extern "C" LiaStreamer* lia_streamer_create(void* const* device_slabs, int n_slots, size_t slab_bytes) {
@@ -74,6 +99,13 @@ extern "C" LiaStreamer* lia_streamer_create(void* const* device_slabs, int n_slo
     s->released.push_back(b);
     s->has_release.push_back(false);
   }
+  for (int i = 0; i < LiaStreamer::TIMING_RING; ++i) {
+    if (cudaEventCreate(&s->t0[i]) != cudaSuccess || cudaEventCreate(&s->t1[i]) != cudaSuccess) {
+      lia_set_error("lia_streamer_create: cudaEventCreate failed");
+      lia_streamer_destroy(s);
+      return nullptr;
+    }
+  }
   return s;
 }
 
@@ -81,14 +113,14 @@ extern "C" int lia_streamer_prefetch(LiaStreamer* s, int slot, const void* host_
   LIA_CHECK_ARG(s && slot >= 0 && slot < (int)s->slabs.size(), "lia_streamer_prefetch: bad slot");
   LIA_CHECK_ARG(host_src && bytes > 0 && bytes <= s->slab_bytes, "lia_streamer_prefetch: %zu bytes do not fit the %zu-byte slab", bytes, s->slab_bytes);
   if (s->has_release[slot]) LIA_CUDA(cudaStreamWaitEvent(s->copy_stream, s->released[slot], 0));
-  cudaEvent_t t0 = nullptr, t1 = nullptr;
-  LIA_CUDA(cudaEventCreate(&t0));
-  LIA_CUDA(cudaEventCreate(&t1));
-  LIA_CUDA(cudaEventRecord(t0, s->copy_stream));
+  const int ti = s->ring_pos;
+  s->ring_pos = (ti + 1) % LiaStreamer::TIMING_RING;
+  s->fold(ti);   // the pair's previous copy was 64 prefetches ago: long complete
+  LIA_CUDA(cudaEventRecord(s->t0[ti], s->copy_stream));
   LIA_CUDA(cudaMemcpyAsync(s->slabs[slot], host_src, bytes, cudaMemcpyHostToDevice, s->copy_stream));
-  LIA_CUDA(cudaEventRecord(t1, s->copy_stream));
+  LIA_CUDA(cudaEventRecord(s->t1[ti], s->copy_stream));
   LIA_CUDA(cudaEventRecord(s->ready[slot], s->copy_stream));
-  s->timing.emplace_back(t0, t1);
+  s->pending[ti] = true;
   s->bytes += (double)bytes;
   return LIA_OK;
 }
@@ -109,13 +141,7 @@ extern "C" int lia_streamer_release(LiaStreamer* s, int slot, lia_stream_t compu
 extern "C" int lia_streamer_stats(LiaStreamer* s, double* bytes, double* copy_ms) {
   LIA_CHECK_ARG(s != nullptr, "lia_streamer_stats: null streamer");
   LIA_CUDA(cudaStreamSynchronize(s->copy_stream));
-  for (auto& pr : s->timing) {
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) s->copy_ms += ms;
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
-  }
-  s->timing.clear();
+  for (int i = 0; i < LiaStreamer::TIMING_RING; ++i) s->fold(i);
   if (bytes) *bytes = s->bytes;
   if (copy_ms) *copy_ms = s->copy_ms;
   return LIA_OK;
@@ -123,10 +149,11 @@ extern "C" int lia_streamer_stats(LiaStreamer* s, double* bytes, double* copy_ms
 
 extern "C" int lia_streamer_destroy(LiaStreamer* s) {
   if (!s) return LIA_OK;
+  RelaxedCaptureMode relaxed;
   if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
-  for (auto& pr : s->timing) {
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
+  for (int i = 0; i < LiaStreamer::TIMING_RING; ++i) {
+    if (s->t0[i]) cudaEventDestroy(s->t0[i]);
+    if (s->t1[i]) cudaEventDestroy(s->t1[i]);
   }
   for (auto e : s->ready) cudaEventDestroy(e);
   for (auto e : s->released) cudaEventDestroy(e);
@@ -144,6 +171,7 @@ static_assert(sizeof(cudaIpcMemHandle_t) == LIA_P2P_HANDLE_BYTES, "LIA_P2P_HANDL
 
 extern "C" int lia_p2p_alloc(size_t bytes, void** dev_ptr, void* handle_out) {
   LIA_CHECK_ARG(bytes > 0 && dev_ptr != nullptr && handle_out != nullptr, "lia_p2p_alloc: bad arguments");
+  RelaxedCaptureMode relaxed;
   void* p = nullptr;
   LIA_CUDA(cudaMalloc(&p, bytes));
   cudaError_t e = cudaMemset(p, 0, bytes);
@@ -173,12 +201,14 @@ extern "C" int lia_p2p_open(const void* handle, void** peer_ptr) {
 
 extern "C" int lia_p2p_close(void* peer_ptr) {
   if (peer_ptr == nullptr) return LIA_OK;
+  RelaxedCaptureMode relaxed;
   LIA_CUDA(cudaIpcCloseMemHandle(peer_ptr));
   return LIA_OK;
 }
 
 extern "C" int lia_p2p_free(void* dev_ptr) {
   if (dev_ptr == nullptr) return LIA_OK;
+  RelaxedCaptureMode relaxed;
   LIA_CUDA(cudaFree(dev_ptr));
   return LIA_OK;
 }

@@ -34,16 +34,22 @@ __global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ 
   }
   p += 2;
   p = p < 0 ? 0 : (p >= max_pos_rows ? max_pos_rows - 1 : p);
-  const bf16* tr = tok + (size_t)id * h;
-  const bf16* pr = pos + (size_t)p * h;
+  // a null table contributes nothing: the row of the other table is copied through unchanged (opt-350m looks its
+  // token rows [e] and position rows [h] up separately; they meet in project_in's residual epilogue, M:1139-1142)
+  const bf16* tr = tok != nullptr ? tok + (size_t)id * h : nullptr;
+  const bf16* pr = pos != nullptr ? pos + (size_t)p * h : nullptr;
   bf16* o = out + (size_t)row * h;
   for (int i = threadIdx.x * 8; i < h; i += 128 * 8) {
-    float a[8], c[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(tr + i)), a);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(pr + i)), c);
+    if (tr != nullptr && pr != nullptr) {
+      float a[8], c[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(tr + i)), a);
+      unpack8(__ldg(reinterpret_cast<const uint4*>(pr + i)), c);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] += c[j];
-    *reinterpret_cast<uint4*>(o + i) = pack8(a);
+      for (int j = 0; j < 8; ++j) a[j] += c[j];
+      *reinterpret_cast<uint4*>(o + i) = pack8(a);
+    } else {
+      *reinterpret_cast<uint4*>(o + i) = __ldg(reinterpret_cast<const uint4*>((tr != nullptr ? tr : pr) + i));
+    }
   }
 }
 
@@ -165,9 +171,11 @@ extern "C" int lia_embed_masked_bf16(const int64_t* ids, const int64_t* attentio
                                      const void* embed_positions, void* out, int B, int S, int h, int past_len, int vocab,
                                      int max_pos_rows, lia_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  LIA_CHECK_ARG(ids && embed_tokens && embed_positions && out, "lia_embed_bf16: null pointer");
+  LIA_CHECK_ARG(ids && out && (embed_tokens || embed_positions), "lia_embed_bf16: null pointer (at most one of the two tables may be null)");
   LIA_CHECK_ARG(B > 0 && S > 0 && h > 0 && h % 8 == 0, "lia_embed_bf16: bad shape B=%d S=%d h=%d", B, S, h);
-  LIA_CHECK_ARG(past_len >= 0 && past_len + S + 2 <= max_pos_rows, "lia_embed_bf16: positions %d..%d exceed the table (%d rows)", past_len + 2, past_len + S + 1, max_pos_rows);
+  LIA_CHECK_ARG(past_len >= 0, "lia_embed_bf16: negative past_len");
+  LIA_CHECK_ARG(embed_tokens == nullptr || vocab > 0, "lia_embed_bf16: vocab must be positive");
+  LIA_CHECK_ARG(embed_positions == nullptr || past_len + S + 2 <= max_pos_rows, "lia_embed_bf16: positions %d..%d exceed the table (%d rows)", past_len + 2, past_len + S + 1, max_pos_rows);
   LIA_CHECK_ARG(attention_mask == nullptr || mask_ld >= past_len + S, "lia_embed_masked_bf16: mask rows hold %d columns, need %d", mask_ld, past_len + S);
   lia_launch(embed_kernel, dim3(B * S), dim3(128), 0, stream, ids, reinterpret_cast<const bf16*>(embed_tokens),
                                            reinterpret_cast<const bf16*>(embed_positions), reinterpret_cast<bf16*>(out), S, h,

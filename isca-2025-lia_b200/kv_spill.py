@@ -13,6 +13,7 @@ no device-wide synchronisation, no per-call allocation.
 """
 import torch
 
+from . import graphs
 from .streamer import HostArena
 
 BF16 = torch.bfloat16
@@ -137,10 +138,9 @@ class KVSpill:
             self.arena = None
 
     def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        # synchronising a stream / freeing pinned memory inside an open graph capture would invalidate it (graphs.py)
+        if getattr(self, "arena", None) is not None:
+            graphs.finalize(self.close)
 
 
 def plan_resident_layers(L, per_layer_bytes, free_bytes, reserve_bytes=4 << 30):

@@ -30,7 +30,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import _lib, ops, tp as tp_mod
+from . import _lib, graphs, ops, tp as tp_mod
 from .ops import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV
 from .kv_spill import KVSpill, plan_resident_layers
 from .streamer import HostArena, LayerStreamer
@@ -358,11 +358,6 @@ class OPTDecoder:
         if tuple(self.embed_tokens.shape) != (cfg.vocab_size, ed) or self.embed_positions.shape[1] != h:
             raise ValueError(f"embedding tables {tuple(self.embed_tokens.shape)} / {tuple(self.embed_positions.shape)} do not "
                              f"match vocab {cfg.vocab_size}, word_embed_proj_dim {ed}, hidden_size {h}")
-        if ed != h:
-            # one-row zero tables: the embed kernel clamps out-of-range ids / positions to the last row, so a lookup
-            # against them contributes +0 and the kernel returns the other table's rows unchanged
-            self._zero_tok = torch.zeros(1, h, dtype=BF16, device=dev)
-            self._zero_pos = torch.zeros(1, ed, dtype=BF16, device=dev)
 
     def embed_rows(self, ids, past_len, mask, out, ws):
         """hidden = project_in(embed_tokens[ids]) + embed_positions[pos]  (M:1107-1142) into ``out`` [B,S,h]."""
@@ -370,8 +365,8 @@ class OPTDecoder:
             return ops.embed(ids, self.embed_tokens, self.embed_positions, past_len, out=out, attention_mask=mask)
         B, S = ids.shape
         h, ed = self.config.hidden_size, self.config.embed_dim
-        tok = ops.embed(ids, self.embed_tokens, self._zero_pos, past_len, attention_mask=mask)     # token rows [B,S,e]
-        pos = ops.embed(ids, self._zero_tok, self.embed_positions, past_len, attention_mask=mask)  # position rows [B,S,h]
+        tok = ops.embed(ids, self.embed_tokens, None, past_len, attention_mask=mask)      # token rows [B,S,e] (no table = +0)
+        pos = ops.embed(ids, None, self.embed_positions, past_len, attention_mask=mask)   # position rows [B,S,h]
         ops.gemm(tok.view(B * S, ed), self.project_in, None, out=out.view(B * S, h), epilogue=EPI_BIAS_RESIDUAL,
                  residual=pos.view(B * S, h), workspace=ws.gemm)                                   # M:1139-1142
         return out
@@ -423,7 +418,9 @@ class OPTDecoder:
         M = nb * S
         ln, q, ctx, ffn = ws.ln[:M], ws.q[:M], ws.ctx[:M], ws.ffn[:M]
         big = M > 128
-        x1 = ws.x1[:M] if big else ws.x1d[:M]
+        # decode (S == 1) keeps its residual stream out of the peer-mapped arena; a short PREFILL (M <= 128, S > 1) has up to
+        # 128 rows and uses the prefill buffer (x1d holds `batch` rows only)
+        x1 = ws.x1d[:M] if S == 1 else ws.x1[:M]
         pre = self.pre_ln
         if pre:
             ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                               # decoder.py:198-204
@@ -702,7 +699,7 @@ class OPTForCausalLM:
                 g = st.graphs.get((t, suppress))
                 if g is None:
                     g = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(g):
+                    with graphs.capture(g):              # GC-quiesced: a finalizer must not invalidate the capture
                         self._decode_step(st, t, suppress)
                     st.graphs[(t, suppress)] = g
                 g.replay()

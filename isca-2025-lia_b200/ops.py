@@ -71,6 +71,12 @@ def gemm(a, w, bias, out=None, epilogue=EPI_BIAS, residual=None, qkv=None, works
         _req(residual, "residual")
     if epilogue != EPI_QKV and out is None:
         out = torch.empty(M, N, dtype=BF16, device=a.device)
+    if epilogue != EPI_QKV:
+        _req(out, "out")
+        if tuple(out.shape) != (M, N):
+            raise _lib.LiaError(f"gemm: out is {tuple(out.shape)}, need ({M}, {N})")
+    if residual is not None and tuple(residual.shape) != (M, N):
+        raise _lib.LiaError(f"gemm: residual is {tuple(residual.shape)}, need ({M}, {N})")
     ws_ptr, ws_bytes = (None, 0)
     if workspace is not None:
         ws_ptr, ws_bytes = workspace.buf.data_ptr(), workspace.buf.numel()
@@ -90,6 +96,8 @@ def gemm_allreduce(a, w, bias, residual, out, tp_args, workspace=None):
     N = w.shape[0]
     if w.shape[1] != K:
         raise _lib.LiaError(f"gemm_allreduce: a is [{M},{K}] but w is {tuple(w.shape)}")
+    if tuple(out.shape) != (M, N) or tuple(residual.shape) != (M, N):
+        raise _lib.LiaError(f"gemm_allreduce: out {tuple(out.shape)} / residual {tuple(residual.shape)}, need ({M}, {N})")
     if bias is not None:
         _req(bias, "bias")
     ws_ptr, ws_bytes = (None, 0)
@@ -102,10 +110,20 @@ def gemm_allreduce(a, w, bias, residual, out, tp_args, workspace=None):
     return out
 
 
+def _check_cache_rows(k_cache, v_cache, rows, what):
+    """The time dimension of the cache bounds every append and every read (the reference's slice assignment
+    A:473-491 raises there)."""
+    if k_cache.dim() != 4 or k_cache.shape != v_cache.shape:
+        raise _lib.LiaError(f"{what}: k_cache {tuple(k_cache.shape)} / v_cache {tuple(v_cache.shape)} must be equal [Tmax,B,H,d]")
+    if rows > k_cache.shape[0]:
+        raise _lib.LiaError(f"{what}: {rows} cached positions exceed the cache's {k_cache.shape[0]} rows")
+
+
 def qkv_args(q_out, k_cache, v_cache, S, pos0, b0, scale):
     """k_cache/v_cache: [Tmax, Bc, H, d] time-major (attentions.py:471-472)."""
     _req(q_out, "q_out"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
     hq = k_cache.shape[2] * k_cache.shape[3]
+    _check_cache_rows(k_cache, v_cache, pos0 + S, "qkv_args")
     return LiaQkvArgs(q_out.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), hq, S, pos0, k_cache.shape[1], b0,
                       float(scale))
 
@@ -115,6 +133,7 @@ def kv_append(q, k, v, k_cache, v_cache, pos0, b0, scale, q_out=None):
     _req(q, "q"); _req(k, "k"); _req(v, "v"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
     B, S = q.shape[0], q.shape[1]
     hq = k_cache.shape[2] * k_cache.shape[3]
+    _check_cache_rows(k_cache, v_cache, pos0 + S, "kv_append")
     if q_out is None:
         q_out = torch.empty_like(q)
     check(_lib.load().lia_kv_append_bf16(_p(q), _p(k), _p(v), _p(q_out), _p(k_cache), _p(v_cache), B, S, hq, pos0,
@@ -127,6 +146,7 @@ def attn_prefill(q, k_cache, v_cache, B, S, b0=0, out=None):
     """Causal attention over rows [0,S) of the cache (attentions.py:444-449, 493-536)."""
     _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
     _, Bc, H, d = k_cache.shape
+    _check_cache_rows(k_cache, v_cache, S, "attn_prefill")
     if out is None:
         out = torch.empty(B * S, H * d, dtype=BF16, device=q.device)
     check(_lib.load().lia_attn_prefill_bf16(_p(q), _p(k_cache), _p(v_cache), _p(_req(out, "out")), B, H, S, d, Bc, b0,
@@ -139,6 +159,7 @@ def attn_decode(q, k_cache, v_cache, B, T, b0=0, out=None, splits=0, workspace=N
     """One query token per sequence over T cached positions, no mask (attentions.py:395-399, 500)."""
     _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
     _, Bc, H, d = k_cache.shape
+    _check_cache_rows(k_cache, v_cache, T, "attn_decode")
     if out is None:
         out = torch.empty(B, H * d, dtype=BF16, device=q.device)
     ws_ptr, ws_bytes = (None, 0)
@@ -159,9 +180,21 @@ def embed(ids, embed_tokens, embed_positions, past_len, out=None, attention_mask
     """Token + learned positional embedding (lia/modeling_opt.py:1107-1142, 368-378).  ``attention_mask``
     (int64 [B, >= past_len + S], may be a column-slice view of a wider buffer) selects the positions the
     reference derives from its cumsum; None means all ones."""
-    _req(ids, "ids", torch.int64); _req(embed_tokens, "embed_tokens"); _req(embed_positions, "embed_positions")
+    _req(ids, "ids", torch.int64)
+    if embed_tokens is None and embed_positions is None:
+        raise _lib.LiaError("embed: at most one of embed_tokens / embed_positions may be None")
+    if embed_tokens is not None:
+        _req(embed_tokens, "embed_tokens")
+    if embed_positions is not None:
+        _req(embed_positions, "embed_positions")
     B, S = ids.shape
-    V, h = embed_tokens.shape
+    V = embed_tokens.shape[0] if embed_tokens is not None else 0
+    h = (embed_tokens if embed_tokens is not None else embed_positions).shape[1]
+    if embed_tokens is not None and embed_positions is not None and embed_positions.shape[1] != h:
+        raise _lib.LiaError(f"embed: token rows are {h} wide but position rows {embed_positions.shape[1]}")
+    P = embed_positions.shape[0] if embed_positions is not None else 0
+    if out is not None and (out.numel() != B * S * h):
+        raise _lib.LiaError(f"embed: out has {out.numel()} elements, need {B * S * h}")
     if out is None:
         out = torch.empty(B, S, h, dtype=BF16, device=ids.device)
     mask_ptr, mask_ld = None, 0
@@ -174,7 +207,7 @@ def embed(ids, embed_tokens, embed_positions, past_len, out=None, attention_mask
             raise _lib.LiaError(f"attention_mask has {am.shape[1]} columns, need past_len + S = {past_len + S}")
         mask_ptr, mask_ld = am.data_ptr(), am.stride(0) if B > 1 else max(am.stride(0), am.shape[1])
     check(_lib.load().lia_embed_masked_bf16(_p(ids), mask_ptr, mask_ld, _p(embed_tokens), _p(embed_positions),
-                                            _p(_req(out, "out")), B, S, h, past_len, V, embed_positions.shape[0], _stream()),
+                                            _p(_req(out, "out")), B, S, h, past_len, V, P, _stream()),
           "lia_embed_masked_bf16")
     count_launches()
     return out

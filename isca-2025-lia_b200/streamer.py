@@ -10,7 +10,7 @@ import ctypes
 
 import torch
 
-from . import _lib
+from . import _lib, graphs
 from ._lib import check
 
 BF16 = torch.bfloat16
@@ -31,14 +31,15 @@ class HostArena:
     def close(self):
         if self.ptr:
             self.tensor = None
-            check(_lib.load().lia_host_arena_free(self.ptr, self.nbytes), "lia_host_arena_free")
-            self.ptr = None
+            ptr, self.ptr = self.ptr, None
+            check(_lib.load().lia_host_arena_free(ptr, self.nbytes), "lia_host_arena_free")
 
     def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        # cudaFreeHost inside somebody's open graph capture would invalidate it: park the free (graphs.py)
+        ptr, nbytes = getattr(self, "ptr", None), getattr(self, "nbytes", 0)
+        if ptr:
+            self.ptr, self.tensor = None, None
+            graphs.finalize(lambda: _lib.load().lia_host_arena_free(ptr, nbytes))
 
 
 class LayerStreamer:
@@ -111,11 +112,16 @@ class LayerStreamer:
 
     def close(self):
         if self.handle:
-            _lib.load().lia_streamer_destroy(self.handle)
-            self.handle = None
+            handle, self.handle = self.handle, None
+            _lib.load().lia_streamer_destroy(handle)
 
     def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass
+        handle = getattr(self, "handle", None)
+        if handle:
+            self.handle = None
+            slots = getattr(self, "slots", None)
+
+            def free(slots=slots):                        # the device slots must outlive the copy stream
+                _lib.load().lia_streamer_destroy(handle)
+                del slots
+            graphs.finalize(free)

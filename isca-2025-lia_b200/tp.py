@@ -17,7 +17,7 @@ import os
 import torch
 import torch.distributed as dist
 
-from . import _lib
+from . import _lib, graphs
 
 _group = None
 
@@ -178,7 +178,6 @@ class PeerArena:
             self.local = None
 
     def __del__(self):
-        try:
-            self.close(sync=False)
-        except Exception:
-            pass
+        # cudaFree / cudaDeviceSynchronize inside an open graph capture would invalidate it: park the free (graphs.py)
+        if getattr(self, "local", None):
+            graphs.finalize(lambda: self.close(sync=False))

@@ -137,14 +137,25 @@ def make(calls):
     def embed(ids, embed_tokens, embed_positions, past_len, out=None, attention_mask=None):
         calls.log.append(("embed", tuple(ids.shape), past_len))
         B, S = ids.shape
-        V, P = embed_tokens.shape[0], embed_positions.shape[0]
+        # the C ABI's argument checks (csrc/misc.cu lia_embed_masked_bf16), so that contract violations fail on CPU too
+        assert embed_tokens is not None or embed_positions is not None
+        assert past_len >= 0 and (embed_positions is None or past_len + S + 2 <= embed_positions.shape[0]), \
+            "positions exceed the table"
+        assert attention_mask is None or attention_mask.shape[1] >= past_len + S
+        V = embed_tokens.shape[0] if embed_tokens is not None else 0
+        P = embed_positions.shape[0] if embed_positions is not None else 0
         if attention_mask is None:
             pos = torch.arange(past_len, past_len + S).expand(B, S)
         else:
             am = attention_mask[:, :past_len + S].long()
             pos = ((torch.cumsum(am, dim=1) * am) - 1)[:, past_len:]
-        pos = (pos + 2).clamp(0, P - 1)                   # the kernel clamps both lookups
-        r = F.embedding(ids.clamp(0, V - 1), embed_tokens) + F.embedding(pos, embed_positions)
+        if embed_positions is None:                       # a null table contributes nothing (rows copied through)
+            r = F.embedding(ids.clamp(0, V - 1), embed_tokens)
+        elif embed_tokens is None:
+            r = F.embedding((pos + 2).clamp(0, P - 1), embed_positions)
+        else:
+            pos = (pos + 2).clamp(0, P - 1)               # the kernel clamps both lookups
+            r = F.embedding(ids.clamp(0, V - 1), embed_tokens) + F.embedding(pos, embed_positions)
         if out is None:
             return r
         out.copy_(r.view(out.shape))

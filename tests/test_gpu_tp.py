@@ -42,7 +42,7 @@ def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, twoshot, monkeypatch)
     if twoshot is not None:
         monkeypatch.setenv("LIA_TP_DECODE_TWOSHOT", twoshot)
     import lia_b200  # noqa: F401
-    from lia_b200 import _lib, ops, tp
+    from lia_b200 import _lib, graphs, ops, tp
     lib = _lib.load()
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     monkeypatch.setenv("LIA_GEMM_MAX_CTAS", str(sms // world))
@@ -86,20 +86,20 @@ def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, twoshot, monkeypatch)
         assert err <= 2 ** -7 * scale, (rep, err, scale)      # a couple of bf16 ulps (K-loop summation order only)
     first = outs[0].clone()
     # CUDA-graph replay: kernel arguments are frozen, epochs advance in device memory
-    graphs = []
+    captured = []
     for r in range(world):
         gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr, stream=streams[r]):
+        with graphs.capture(gr, stream=streams[r]):       # GC-quiesced capture that surfaces errors raised inside it
             ops.gemm_allreduce(As[r], Ws[r], bs[r], res, outs[r], arenas[r].args(outs[r] if M > 128 else None),
                                workspace=wss[r])
-        graphs.append(gr)
+        captured.append(gr)
     for rep in range(2):
         for o in outs:
             o.zero_()
         torch.cuda.synchronize()
         for r in range(world):
             with torch.cuda.stream(streams[r]):
-                graphs[r].replay()
+                captured[r].replay()
         torch.cuda.synchronize()
         for a in arenas:
             a.check()
@@ -108,6 +108,66 @@ def test_fused_allreduce_two_ranks_one_gpu(world, M, N, K, twoshot, monkeypatch)
     for a in arenas:
         a._opened = []
         a.close(sync=False)
+
+
+def test_finalizers_do_not_invalidate_capture():
+    """GPUTEST_r01's failure mode: Python's cyclic GC fires in the middle of somebody's graph capture and a dead
+    resource holder's finalizer calls cudaFreeHost / cudaFree / cudaStreamDestroy -> cudaErrorStreamCaptureInvalidated
+    at capture_end.  Finalizers must park their frees while a capture is open (lia_b200/graphs.py), also for captures
+    opened with plain torch.cuda.graph."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a GPU")
+    import gc
+    import lia_b200  # noqa: F401
+    from lia_b200 import graphs, ops, tp
+    from lia_b200.kv_spill import KVSpill
+    from lia_b200.streamer import HostArena, LayerStreamer
+    from lia_b200.weights import LayerLayout
+    dev = torch.device("cuda:0")
+
+    def make_garbage():
+        lay = LayerLayout(64, 256, 1, heads=1)
+        host = HostArena(lay.numel * 2)
+        slabs = [host.tensor[i * lay.numel:(i + 1) * lay.numel] for i in range(2)]
+        st = LayerStreamer(lay, slabs, dev)
+        st.begin()
+        sp = KVSpill(2, 8, 2, 1, 64, dev)
+        ar = tp.PeerArena(0, 2, dev, 4096, [("out", 4096)], exchange=lambda mine: [0, 0])
+        cyc = [host, st, sp, ar]
+        cyc.append(cyc)                                   # only the cyclic collector can free these
+
+    x = torch.randn(64, 256, device=dev).to(BF16)
+    w = torch.randn(256, 256, device=dev).to(BF16)
+    b = torch.zeros(256, device=dev, dtype=BF16)
+    out = torch.empty(64, 256, device=dev, dtype=BF16)
+    ws = ops.GemmWorkspace(ops.GemmWorkspace.bytes_for([(64, 256, 256)]), dev)
+    want = ops.gemm(x, w, b, workspace=ws).clone()
+    torch.cuda.synchronize()
+    gc.collect()
+    for how in ("torch", "ours"):
+        make_garbage()
+        g = torch.cuda.CUDAGraph()
+        if how == "torch":                                # a foreign capture: only the finalizers' own check protects it
+            with torch.cuda.graph(g):
+                gc.collect()                              # fires the finalizers inside the capture
+                ops.gemm(x, w, b, out=out, workspace=ws)
+            assert graphs._deferred, "finalizers ran inside the capture instead of being parked"
+            graphs.drain()
+        else:
+            with graphs.capture(g):                       # collects before opening, keeps the collector off inside
+                ops.gemm(x, w, b, out=out, workspace=ws)
+        assert not graphs._deferred
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, want), how
+    # an exception raised inside the block is what the caller sees, not the capture_end error that follows from it
+    g = torch.cuda.CUDAGraph()
+    with pytest.raises(ZeroDivisionError):
+        with graphs.capture(g):
+            ops.gemm(x, w, b, out=out, workspace=ws)
+            1 / 0
+    torch.cuda.synchronize()
 
 
 @pytest.mark.parametrize("nproc", [2])

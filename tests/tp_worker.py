@@ -21,7 +21,7 @@ BF16 = torch.bfloat16
 
 def main():
     import lia_b200
-    from lia_b200 import _lib, ops, tp
+    from lia_b200 import _lib, graphs, ops, tp
     rank, world = tp.init_from_env("nccl")
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
     torch.cuda.set_device(dev)
@@ -52,7 +52,7 @@ def main():
             arena.check()
             assert torch.equal(out, want), (rank, M, N, K, rep, (out.float() - want.float()).abs().max().item())
         gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
+        with graphs.capture(gr):
             ops.gemm_allreduce(a, w, b, res, out, args, workspace=ws)
         for rep in range(2):
             out.zero_()
@@ -72,7 +72,21 @@ def main():
     # ---- 2. model level
     cfg = lia_b200.OPTConfig(hidden_size=512, num_hidden_layers=4, num_attention_heads=8, ffn_dim=2048, vocab_size=1024,
                              max_position_embeddings=128)
-    B, S, new, nmb = 8, 40, 8, 2
+    # (8, 40, nmb 2): 160-row prefill blocks (two-shot, M > 128); (4, 24, nmb 1): a 96-row prefill, which runs on the
+    # decode-shaped (swap-AB, M <= 128) kernels with S > 1 -- the case that overran the decode residual buffer in round 1
+    for (B, S, new, nmb) in [(8, 40, 8, 2), (4, 24, 6, 1)]:
+        _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb)
+    dist.barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        print("TP_WORKER_OK", flush=True)
+    sys.stdout.flush()
+    # CUDA graphs that captured NCCL kernels may still be alive in garbage: tearing the communicator down
+    # under them can block, so leave without the orderly destroy (the work is done and checked)
+    os._exit(0)
+
+
+def _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb):
     ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(3))
     one = lia_b200.OPTForCausalLM(cfg, dev).init_weights(seed=5, bias_std=0.02, ln_std=0.05)
     st1 = one._state(B, S, new, nmb)
@@ -102,21 +116,13 @@ def main():
         assert all(torch.equal(alls[0], x) for x in alls), "ranks disagree on greedy tokens"
         if rank == 0:
             agree = (toks[0].cpu() == tok_ref.cpu()).float().mean().item()
-            print(f"TP{world} fused={fused}: prefill hidden rel err {err:.2e}; token agreement with TP1 {agree:.3f}; "
+            print(f"TP{world} fused={fused} B={B} S={S} nmb={nmb}: prefill hidden rel err {err:.2e}; token agreement with TP1 {agree:.3f}; "
                   f"decode {1e3 * sum(m.last_timing['decode_s']) / (new - 1):.3f} ms/step", flush=True)
         for s_ in m._states.values():
             if s_.arena is not None:
                 s_.arena.close()
         m._states.clear()
         del m, st, toks
-    dist.barrier()
-    torch.cuda.synchronize()
-    if rank == 0:
-        print("TP_WORKER_OK", flush=True)
-    sys.stdout.flush()
-    # CUDA graphs that captured NCCL kernels may still be alive in garbage: tearing the communicator down
-    # under them can block, so leave without the orderly destroy (the work is done and checked)
-    os._exit(0)
 
 
 if __name__ == "__main__":
