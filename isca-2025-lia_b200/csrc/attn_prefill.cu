@@ -3,9 +3,9 @@
 // Replaces attentions.py:444-449 (mask rebuild), 493-496 (3 transposes), 499-512 (bmm, mask add,
 // clamp, softmax with materialised [B,H,S,S] scores), 529 (bmm).
 //
-// Attention is <= 0.5 % of the prefill FLOPs at S <= 512, so this kernel is a
-// register-resident flash-style kernel on mma.sync.m16n8k16 (tensor cores, fp32 accumulate)
-// rather than a tcgen05 pipeline; the prefill budget is in the projections (gemm_sm100.cu).
+// FIRST-GENERATION kernel, kept as the A/B baseline (LIA_ATTN_PREFILL_TC=0) of the tcgen05 kernel in
+// attn_prefill_sm100.cu, which is the default: a register-resident flash-style kernel on mma.sync.m16n8k16
+// (measured 78 TFLOP/s at B32 H56 S256 d128 -- 5 % of the tensor peak, profiles/r2/r2_ab_attn_prefill.log).
 //
 // To reproduce the reference's rounding points exactly, softmax is done in TWO passes over the
 // keys instead of with online rescaling:
@@ -41,18 +41,7 @@ __device__ __forceinline__ void mma_bf16(float* c, const uint32_t* a, uint32_t b
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Softmax arithmetic.  Default: expf and a true division, as the reference's softmax kernel computes in fp32.  FAST
-// (opt-in, LIA_ATTN_FASTMATH=1, until its parity tests have run on hardware): ex2.approx-based __expf and a multiply by
-// the reciprocal of the row sum -- a few fp32 ulps before the SAME bf16 rounding points, for several times fewer
-// instructions in what is the ALU-bound part of this kernel.
-template <bool FAST>
-__device__ __forceinline__ float exp_(float x) { return FAST ? __expf(x) : expf(x); }
-template <bool FAST>
-__device__ __forceinline__ float prob_(float s, float m, float l, float inv_l) {
-  return FAST ? __expf(s - m) * inv_l : expf(s - m) / l;
-}
-
-template <int D, bool FAST>
+template <int D>
 __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
                                                                const bf16* __restrict__ vc, bf16* __restrict__ out,
                                                                int H, int S, int cache_batch, int b0) {
@@ -167,18 +156,18 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
     float a0 = 0.f, a1 = 0.f;
     if (n0 > -INFINITY) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) a0 += exp_<FAST>(s[nt][0] - n0) + exp_<FAST>(s[nt][1] - n0);
+      for (int nt = 0; nt < 8; ++nt) a0 += expf(s[nt][0] - n0) + expf(s[nt][1] - n0);
     }
     if (n1 > -INFINITY) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt) a1 += exp_<FAST>(s[nt][2] - n1) + exp_<FAST>(s[nt][3] - n1);
+      for (int nt = 0; nt < 8; ++nt) a1 += expf(s[nt][2] - n1) + expf(s[nt][3] - n1);
     }
     a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
     a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
     a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
     a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-    l0 = (m0 > -INFINITY ? l0 * exp_<FAST>(m0 - n0) : 0.f) + a0;
-    l1 = (m1 > -INFINITY ? l1 * exp_<FAST>(m1 - n1) : 0.f) + a1;
+    l0 = (m0 > -INFINITY ? l0 * expf(m0 - n0) : 0.f) + a0;
+    l1 = (m1 > -INFINITY ? l1 * expf(m1 - n1) : 0.f) + a1;
     m0 = n0;
     m1 = n1;
     __syncthreads();
@@ -205,10 +194,10 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
     uint32_t pf[4][4];   // P as A-fragments: 4 k-steps of 16 keys
 #pragma unroll
     for (int k2 = 0; k2 < 4; ++k2) {
-      pf[k2][0] = pack_bf16x2(prob_<FAST>(s[2 * k2][0], mm0, ll0, il0), prob_<FAST>(s[2 * k2][1], mm0, ll0, il0));
-      pf[k2][1] = pack_bf16x2(prob_<FAST>(s[2 * k2][2], mm1, ll1, il1), prob_<FAST>(s[2 * k2][3], mm1, ll1, il1));
-      pf[k2][2] = pack_bf16x2(prob_<FAST>(s[2 * k2 + 1][0], mm0, ll0, il0), prob_<FAST>(s[2 * k2 + 1][1], mm0, ll0, il0));
-      pf[k2][3] = pack_bf16x2(prob_<FAST>(s[2 * k2 + 1][2], mm1, ll1, il1), prob_<FAST>(s[2 * k2 + 1][3], mm1, ll1, il1));
+      pf[k2][0] = pack_bf16x2((expf(s[2 * k2][0] - mm0) / ll0), (expf(s[2 * k2][1] - mm0) / ll0));
+      pf[k2][1] = pack_bf16x2((expf(s[2 * k2][2] - mm1) / ll1), (expf(s[2 * k2][3] - mm1) / ll1));
+      pf[k2][2] = pack_bf16x2((expf(s[2 * k2 + 1][0] - mm0) / ll0), (expf(s[2 * k2 + 1][1] - mm0) / ll0));
+      pf[k2][3] = pack_bf16x2((expf(s[2 * k2 + 1][2] - mm1) / ll1), (expf(s[2 * k2 + 1][3] - mm1) / ll1));
     }
     const uint32_t vbase = smem_u32(sV + (j & 1) * TILE_ELEMS);
 #pragma unroll
@@ -236,237 +225,32 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// Variant for S <= 64*NT (NT = 4: S <= 256, the headline prompt length), OPT-IN until it has been A/B-checked on
-// hardware (LIA_ATTN_PREFILL_KEEP=1; scripts/ab_attn_prefill.py): the bf16-rounded scores of pass 1 stay in
-// REGISTERS (two per 32-bit register: 16 query rows x 256 keys per warp = 64 registers per thread), so pass 2 needs
-// neither the second Q.K^T nor the second read of K -- a third of the kernel's MMAs and half of its shared-memory
-// traffic.  The numbers are the same by construction: pass 2 consumes exactly the values score_tile() produced
-// (rounded to bf16, masked to -inf) instead of recomputing them, and m, l, p and O are formed as above.
-template <int D, int NT, bool FAST>
-__global__ void __launch_bounds__(THREADS, 3) attn_prefill_keep_kernel(const bf16* __restrict__ q, const bf16* __restrict__ kc,
-                                                                    const bf16* __restrict__ vc, bf16* __restrict__ out,
-                                                                    int H, int S, int cache_batch, int b0) {
-  pdl_launch_dependents();
-  pdl_wait();
-  constexpr int PITCH = D + 8;
-  constexpr int TILE_ELEMS = TILE * PITCH;
-  constexpr int KSTEPS = D / 16;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  bf16* sT = reinterpret_cast<bf16*>(smem_raw);            // [2][TILE][PITCH]: K tiles in pass 1, V tiles in pass 2
-
-  const int qi = gridDim.x - 1 - blockIdx.x;               // heaviest (most keys) tiles first; qi < NT
-  const int hh = blockIdx.y;
-  const int b = blockIdx.z;
-  const int q0 = qi * TILE;
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int g = lane >> 2;
-  const int tq = lane & 3;
-  const int row0 = q0 + warp * 16 + g;
-  const int row1 = row0 + 8;
-  const size_t kv_row_stride = (size_t)cache_batch * H * D;
-  const size_t kv_base = ((size_t)(b0 + b) * H + hh) * D;
-
-  uint32_t qf[KSTEPS][4];
-  {
-    const bf16* q_r0 = q + ((size_t)(b * S + row0) * H + hh) * D;
-    const bf16* q_r1 = q + ((size_t)(b * S + row1) * H + hh) * D;
-#pragma unroll
-    for (int kk = 0; kk < KSTEPS; ++kk) {
-      const int c = kk * 16 + tq * 2;
-      qf[kk][0] = row0 < S ? *reinterpret_cast<const uint32_t*>(q_r0 + c) : 0u;
-      qf[kk][1] = row1 < S ? *reinterpret_cast<const uint32_t*>(q_r1 + c) : 0u;
-      qf[kk][2] = row0 < S ? *reinterpret_cast<const uint32_t*>(q_r0 + c + 8) : 0u;
-      qf[kk][3] = row1 < S ? *reinterpret_cast<const uint32_t*>(q_r1 + c + 8) : 0u;
-    }
-  }
-
-  auto load_tile = [&](int stage, int j, const bf16* src) {
-    constexpr int CPR = D / 8;
-    for (int idx = threadIdx.x; idx < TILE * CPR; idx += THREADS) {
-      const int r = idx / CPR;
-      const int c = idx - r * CPR;
-      const int t = j * TILE + r;
-      bf16* dst = sT + stage * TILE_ELEMS + r * PITCH + c * 8;
-      if (t < S) cp_async16(smem_u32(dst), src + (size_t)t * kv_row_stride + kv_base + c * 8);
-      else *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-    }
-    cp_async_commit();
-  };
-
-  // ---------------- pass 1: scores (kept, packed bf16x2), row max and sum of exponentials
-  uint32_t sk[NT][8][2];   // sk[j][nt][0] = {s(row0,key), s(row0,key+1)}, [1] = the same for row1
-  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-  load_tile(0, 0, kc);
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    if (j <= qi) {                                         // uniform over the CTA
-      if (j < qi) {
-        load_tile((j + 1) & 1, j + 1, kc);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      float s[8][4];
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-      const uint32_t kbase = smem_u32(sT + (j & 1) * TILE_ELEMS);
-#pragma unroll
-      for (int kk = 0; kk < KSTEPS; ++kk) {
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t r0, r1, r2, r3;
-          const int krow = np * 16 + (lane >> 4) * 8 + (lane & 7);
-          const int kcol = kk * 16 + ((lane >> 3) & 1) * 8;
-          ldmatrix_x4(kbase + (krow * PITCH + kcol) * 2, r0, r1, r2, r3);
-          mma_bf16(s[2 * np], qf[kk], r0, r1);
-          mma_bf16(s[2 * np + 1], qf[kk], r2, r3);
-        }
-      }
-      float t0 = -INFINITY, t1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt) {
-        const int key = j * TILE + nt * 8 + tq * 2;
-        s[nt][0] = (key <= row0) ? bf16r(s[nt][0]) : -INFINITY;
-        s[nt][1] = (key + 1 <= row0) ? bf16r(s[nt][1]) : -INFINITY;
-        s[nt][2] = (key <= row1) ? bf16r(s[nt][2]) : -INFINITY;
-        s[nt][3] = (key + 1 <= row1) ? bf16r(s[nt][3]) : -INFINITY;
-        sk[j][nt][0] = pack_bf16x2(s[nt][0], s[nt][1]);    // exact: the values are already bf16 (or -inf)
-        sk[j][nt][1] = pack_bf16x2(s[nt][2], s[nt][3]);
-        t0 = fmaxf(t0, fmaxf(s[nt][0], s[nt][1]));
-        t1 = fmaxf(t1, fmaxf(s[nt][2], s[nt][3]));
-      }
-      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 1));
-      t0 = fmaxf(t0, __shfl_xor_sync(0xffffffffu, t0, 2));
-      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 1));
-      t1 = fmaxf(t1, __shfl_xor_sync(0xffffffffu, t1, 2));
-      const float n0 = fmaxf(m0, t0), n1 = fmaxf(m1, t1);
-      float a0 = 0.f, a1 = 0.f;
-      if (n0 > -INFINITY) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) a0 += exp_<FAST>(s[nt][0] - n0) + exp_<FAST>(s[nt][1] - n0);
-      }
-      if (n1 > -INFINITY) {
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) a1 += exp_<FAST>(s[nt][2] - n1) + exp_<FAST>(s[nt][3] - n1);
-      }
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 1);
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 2);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
-      l0 = (m0 > -INFINITY ? l0 * exp_<FAST>(m0 - n0) : 0.f) + a0;
-      l1 = (m1 > -INFINITY ? l1 * exp_<FAST>(m1 - n1) : 0.f) + a1;
-      m0 = n0;
-      m1 = n1;
-      __syncthreads();
-    }
-  }
-  const float mm0 = m0 > -INFINITY ? m0 : 0.f, mm1 = m1 > -INFINITY ? m1 : 0.f;
-  const float ll0 = l0 > 0.f ? l0 : 1.f, ll1 = l1 > 0.f ? l1 : 1.f;
-  const float il0 = 1.f / ll0, il1 = 1.f / ll1;
-
-  // ---------------- pass 2: p = bf16(exp(s-m)/l) from the kept scores, O += p.v (V tiles only)
-  float o[D / 8][4];
-#pragma unroll
-  for (int nt = 0; nt < D / 8; ++nt) o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
-  load_tile(0, 0, vc);
-#pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    if (j <= qi) {
-      if (j < qi) {
-        load_tile((j + 1) & 1, j + 1, vc);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-      uint32_t pf[4][4];
-#pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
-        float a, c;
-        unpack_bf16x2(sk[j][2 * k2][0], a, c);
-        pf[k2][0] = pack_bf16x2(prob_<FAST>(a, mm0, ll0, il0), prob_<FAST>(c, mm0, ll0, il0));
-        unpack_bf16x2(sk[j][2 * k2][1], a, c);
-        pf[k2][1] = pack_bf16x2(prob_<FAST>(a, mm1, ll1, il1), prob_<FAST>(c, mm1, ll1, il1));
-        unpack_bf16x2(sk[j][2 * k2 + 1][0], a, c);
-        pf[k2][2] = pack_bf16x2(prob_<FAST>(a, mm0, ll0, il0), prob_<FAST>(c, mm0, ll0, il0));
-        unpack_bf16x2(sk[j][2 * k2 + 1][1], a, c);
-        pf[k2][3] = pack_bf16x2(prob_<FAST>(a, mm1, ll1, il1), prob_<FAST>(c, mm1, ll1, il1));
-      }
-      const uint32_t vbase = smem_u32(sT + (j & 1) * TILE_ELEMS);
-#pragma unroll
-      for (int k2 = 0; k2 < 4; ++k2) {
-#pragma unroll
-        for (int dp = 0; dp < D / 16; ++dp) {
-          uint32_t r0, r1, r2, r3;
-          const int vrow = k2 * 16 + ((lane >> 3) & 1) * 8 + (lane & 7);
-          const int vcol = dp * 16 + (lane >> 4) * 8;
-          ldmatrix_x4_trans(vbase + (vrow * PITCH + vcol) * 2, r0, r1, r2, r3);
-          mma_bf16(o[2 * dp], pf[k2], r0, r1);
-          mma_bf16(o[2 * dp + 1], pf[k2], r2, r3);
-        }
-      }
-      __syncthreads();
-    }
-  }
-
-  bf16* o_r0 = out + ((size_t)(b * S + row0) * H + hh) * D;
-  bf16* o_r1 = out + ((size_t)(b * S + row1) * H + hh) * D;
-#pragma unroll
-  for (int nt = 0; nt < D / 8; ++nt) {
-    const int c = nt * 8 + tq * 2;
-    if (row0 < S) *reinterpret_cast<uint32_t*>(o_r0 + c) = pack_bf16x2(o[nt][0], o[nt][1]);
-    if (row1 < S) *reinterpret_cast<uint32_t*>(o_r1 + c) = pack_bf16x2(o[nt][2], o[nt][3]);
-  }
-}
-
-constexpr int KEEP_TILES = 4;   // scores of up to 4 x 64 keys stay in registers
-
-bool fastmath_enabled() {   // read per call so that one process can A/B
-  const char* e = getenv("LIA_ATTN_FASTMATH");
-  return e != nullptr && atoi(e) != 0;
-}
-
-bool keep_enabled() {   // read per call (like LIA_GEMM_2CTA) so that one process can A/B the two kernels
-  const char* e = getenv("LIA_ATTN_PREFILL_KEEP");
-  return e != nullptr && atoi(e) != 0;
-}
-
-template <int D, bool FAST>
-int launch_prefill_keep(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
-                        cudaStream_t stream) {
-  constexpr int SMEM = 2 * TILE * (D + 8) * 2;
-  auto kern = attn_prefill_keep_kernel<D, KEEP_TILES, FAST>;
-  static bool configured = false;
-  if (!configured) {
-    LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
-  }
-  const dim3 grid((S + TILE - 1) / TILE, H, B);
-  lia_launch(kern, dim3(grid), dim3(THREADS), SMEM, stream, q, kc, vc, out, H, S, cache_batch, b0);
-  LIA_LAUNCH_CHECK();
-  return LIA_OK;
-}
-
-template <int D, bool FAST>
+template <int D>
 int launch_prefill(const bf16* q, const bf16* kc, const bf16* vc, bf16* out, int B, int H, int S, int cache_batch, int b0,
                    cudaStream_t stream) {
   constexpr int SMEM = 2 * 2 * TILE * (D + 8) * 2;
-  auto kern = attn_prefill_kernel<D, FAST>;
+  auto kern = attn_prefill_kernel<D>;
   static bool configured = false;
   if (!configured) {
     LIA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     configured = true;
   }
   const dim3 grid((S + TILE - 1) / TILE, H, B);
-  lia_launch(kern, dim3(grid), dim3(THREADS), SMEM, stream, q, kc, vc, out, H, S, cache_batch, b0);
-  LIA_LAUNCH_CHECK();
+  LIA_CUDA(lia_launch(kern, dim3(grid), dim3(THREADS), SMEM, stream, q, kc, vc, out, H, S, cache_batch, b0));
   return LIA_OK;
 }
 
+// The tcgen05 kernel (attn_prefill_sm100.cu) is the default; LIA_ATTN_PREFILL_TC=0 selects the mma.sync kernel above
+// for A/B runs (read per call so that one process can compare the two).
+bool tc_enabled() {
+  const char* e = getenv("LIA_ATTN_PREFILL_TC");
+  return e == nullptr || atoi(e) != 0;
+}
+
 }  // namespace
+
+int lia_attn_prefill_tc(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int S, int d,
+                        int cache_batch, int b0, int t_rows, cudaStream_t stream);   // attn_prefill_sm100.cu
 
 extern "C" int lia_attn_prefill_bf16(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H,
                                      int S, int d, int cache_batch, int b0, lia_stream_t stream_) {
@@ -476,19 +260,13 @@ extern "C" int lia_attn_prefill_bf16(const void* q, const void* k_cache, const v
   LIA_CHECK_ARG(B > 0 && H > 0 && S > 0, "lia_attn_prefill_bf16: B,H,S must be positive");
   LIA_CHECK_ARG(B <= 65535 && H <= 65535, "lia_attn_prefill_bf16: B,H exceed grid limits");
   LIA_CHECK_ARG(b0 >= 0 && b0 + B <= cache_batch, "lia_attn_prefill_bf16: batch window [%d,%d) outside cache batch %d", b0, b0 + B, cache_batch);
+  const bool aligned = ((uintptr_t)q % 16 == 0) && ((uintptr_t)k_cache % 16 == 0) && ((uintptr_t)v_cache % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (tc_enabled() && aligned)   // rows [0, S) of the caches are all the tensor maps describe: later rows read as zeros
+    return lia_attn_prefill_tc(q, k_cache, v_cache, out, B, H, S, d, cache_batch, b0, S, stream);
   const bf16* qp = reinterpret_cast<const bf16*>(q);
   const bf16* kp = reinterpret_cast<const bf16*>(k_cache);
   const bf16* vp = reinterpret_cast<const bf16*>(v_cache);
   bf16* op = reinterpret_cast<bf16*>(out);
-  const bool fast = fastmath_enabled();
-  if (S <= TILE * KEEP_TILES && keep_enabled()) {   // opt-in: scores kept in registers between the two passes
-    if (d == 128) return fast ? launch_prefill_keep<128, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
-                              : launch_prefill_keep<128, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
-    return fast ? launch_prefill_keep<64, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
-                : launch_prefill_keep<64, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
-  }
-  if (d == 128) return fast ? launch_prefill<128, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
-                            : launch_prefill<128, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
-  return fast ? launch_prefill<64, true>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream)
-              : launch_prefill<64, false>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+  if (d == 128) return launch_prefill<128>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
+  return launch_prefill<64>(qp, kp, vp, op, B, H, S, cache_batch, b0, stream);
 }

@@ -153,33 +153,6 @@ def test_attn_prefill(ops, B, S, H, d, b0, Bc):
     close_bf16(out, ref, ulps=3.01, what=f"prefill attn S={S} d={d}", scale=ref.abs().amax(-1, keepdim=True))
 
 
-@pytest.mark.skipif(os.environ.get("LIA_TEST_OPTIN", "0") == "0",
-                    reason="opt-in kernel variants (not yet defaults): run with LIA_TEST_OPTIN=1, as scripts/gpu_round2.sh does")
-@pytest.mark.parametrize("keep,fast", [("1", "0"), ("0", "1"), ("1", "1")])
-@pytest.mark.parametrize("B,S,H,d,b0,Bc", [(2, 5, 1, 128, 0, 2), (3, 8, 2, 64, 1, 5), (2, 64, 3, 128, 0, 2), (2, 65, 2, 64, 0, 2),
-                                          (2, 256, 4, 128, 2, 4), (1, 200, 2, 64, 0, 1), (1, 512, 2, 128, 0, 1), (32, 256, 56, 128, 0, 32)])
-def test_attn_prefill_optin_variants(ops, monkeypatch, B, S, H, d, b0, Bc, keep, fast):
-    """LIA_ATTN_PREFILL_KEEP=1 (pass-1 scores stay in registers, S <= 256; otherwise the default kernel runs) must be
-    bit-identical to the default kernel; LIA_ATTN_FASTMATH=1 (__expf, multiply by 1/l) must meet the same tolerance against
-    the fp32 reference with the reference's rounding points as the default kernel does."""
-    q = rnd(B, S, H, d, std=0.3, seed=1)
-    kc = rnd(S + 3, Bc, H, d, seed=2)
-    vc = rnd(S + 3, Bc, H, d, seed=3)
-    monkeypatch.setenv("LIA_ATTN_PREFILL_KEEP", "0")
-    monkeypatch.setenv("LIA_ATTN_FASTMATH", "0")
-    base = ops.attn_prefill(q.view(B * S, H * d), kc, vc, B, S, b0)
-    monkeypatch.setenv("LIA_ATTN_PREFILL_KEEP", keep)
-    monkeypatch.setenv("LIA_ATTN_FASTMATH", fast)
-    out = ops.attn_prefill(q.view(B * S, H * d), kc, vc, B, S, b0)
-    torch.cuda.synchronize()
-    if fast == "0":
-        assert torch.equal(out, base), f"keep-scores kernel differs from the default at S={S} d={d}"
-    else:
-        ref = attn_ref(q.permute(0, 2, 1, 3), kc[:S, b0:b0 + B].permute(1, 2, 0, 3), vc[:S, b0:b0 + B].permute(1, 2, 0, 3), True)
-        ref = ref.permute(0, 2, 1, 3).reshape(B * S, H * d)
-        close_bf16(out, ref, ulps=3.01, what=f"prefill attn (fast-math) S={S} d={d}", scale=ref.abs().amax(-1, keepdim=True))
-
-
 @pytest.mark.parametrize("B,T,H,d,b0,Bc,splits", [(2, 1, 1, 128, 0, 2, 1), (3, 9, 2, 64, 1, 5, 1), (64, 288, 8, 128, 0, 64, 1),
                                                  (2, 1000, 4, 128, 0, 2, 0), (1, 2048, 2, 64, 0, 1, 0), (4, 300, 4, 128, 4, 8, 3)])
 def test_attn_decode(ops, B, T, H, d, b0, Bc, splits):
