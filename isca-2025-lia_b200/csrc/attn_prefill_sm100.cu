@@ -31,10 +31,12 @@ namespace {
 
 constexpr int BM = 128;              // queries per tile = TMEM lanes = UMMA M
 constexpr int BN = 128;              // keys per block
-constexpr int SOFTMAX_THREADS = 256;
-constexpr int PRODUCER_WARP = 8;
+constexpr int QK_PRODUCER_WARP = 8;
 constexpr int MMA_WARP = 9;
-constexpr int THREADS = 320;
+constexpr int V_PRODUCER_WARP = 10;
+constexpr int THREADS = 352;
+constexpr int S_BUFS = 3;            // score buffers in TMEM (128 columns each)
+constexpr int RESIDENT_BLOCKS = 2;   // items with at most this many key blocks keep their scores in TMEM between the passes
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float M_INIT = -1.0e30f;   // finite "no key seen yet": keeps (m_old - m_new) and (s - m) free of inf - inf
 
@@ -43,15 +45,15 @@ struct Layout {
   static constexpr int SLABS = D / 64;               // 64-element (128-byte) wide column slabs per row
   static constexpr int SLAB_BYTES = BM * 128;        // 128 rows x 128 bytes
   static constexpr int TILE_BYTES = SLABS * SLAB_BYTES;
-  static constexpr int Q_OFF = 0;
-  static constexpr int K_OFF = Q_OFF + TILE_BYTES;           // 2 stages
-  static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;       // 2 stages
-  static constexpr int P_OFF = V_OFF + 2 * TILE_BYTES;       // [128 queries][128 keys] bf16 = 2 slabs
+  static constexpr int Q_OFF = 0;                            // 2 buffers (item parity)
+  static constexpr int K_OFF = Q_OFF + 2 * TILE_BYTES;       // 2 stages
+  static constexpr int V_OFF = K_OFF + 2 * TILE_BYTES;       // 1 stage
+  static constexpr int P_OFF = V_OFF + TILE_BYTES;           // [128 queries][128 keys] bf16 = 2 slabs
   static constexpr int STAT_OFF = P_OFF + 2 * SLAB_BYTES;    // float2 [2 item parities][2 column halves][128 rows]
   static constexpr int BAR_OFF = STAT_OFF + 2 * 2 * BM * 8;
-  static constexpr int NUM_BARS = 18;
+  static constexpr int NUM_BARS = 20;
   static constexpr int TOTAL = BAR_OFF + NUM_BARS * 8 + 16 + 1024 /* alignment slack */;
-  static constexpr int O_COL = 2 * BN;                       // TMEM: S[0] | S[1] | O
+  static constexpr int O_COL = S_BUFS * BN;                  // TMEM: S[0] | S[1] | S[2] | O
 };
 
 __device__ __forceinline__ float ex2(float x) {
@@ -59,10 +61,37 @@ __device__ __forceinline__ float ex2(float x) {
   asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+// the two warps that share a row range (w and w + 4) meet on their own 64-thread named barrier: ids 2..5
+__device__ __forceinline__ void pair_bar_sync(int wq) { asm volatile("bar.sync %0, 64;" ::"r"(2 + wq) : "memory"); }
+// non-blocking probe of an mbarrier phase (the MMA thread serves two independent job streams)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+      "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]),
+      "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 struct Item {
   int b, hh, qt, nblk;
+  bool resident;            // scores (as exponentials) stay in TMEM between the passes: no second Q.K^T, no second ex2
+  int qk_jobs;              // Q.K^T launches: nblk (resident) or 2 * nblk (recomputed in pass 2)
 };
 __device__ __forceinline__ Item decode_item(int idx, int bh_count, int H, int nq) {
   Item it;
@@ -71,6 +100,8 @@ __device__ __forceinline__ Item decode_item(int idx, int bh_count, int H, int nq
   it.b = bh / H;
   it.hh = bh - it.b * H;
   it.nblk = it.qt + 1;                        // causal: key blocks 0..qt
+  it.resident = it.nblk <= RESIDENT_BLOCKS;
+  it.qk_jobs = it.resident ? it.nblk : 2 * it.nblk;
   return it;
 }
 
@@ -84,34 +115,36 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const uint32_t bar_base = smem_base + L::BAR_OFF;
-  // barrier map
-  const uint32_t q_full = bar_base, q_empty = bar_base + 8;
-  auto k_full = [&](int s) { return bar_base + 16 + 8u * s; };
-  auto k_empty = [&](int s) { return bar_base + 32 + 8u * s; };
-  auto v_full = [&](int s) { return bar_base + 48 + 8u * s; };
-  auto v_empty = [&](int s) { return bar_base + 64 + 8u * s; };
-  auto s_full = [&](int s) { return bar_base + 80 + 8u * s; };
-  auto s_empty = [&](int s) { return bar_base + 96 + 8u * s; };
-  const uint32_t p_full = bar_base + 112, p_empty = bar_base + 120, o_full = bar_base + 128, o_empty = bar_base + 136;
+  // barrier map (8 bytes each)
+  auto q_full = [&](int s) { return bar_base + 8u * s; };
+  auto q_empty = [&](int s) { return bar_base + 16 + 8u * s; };
+  auto k_full = [&](int s) { return bar_base + 32 + 8u * s; };
+  auto k_empty = [&](int s) { return bar_base + 48 + 8u * s; };
+  auto s_full = [&](int s) { return bar_base + 64 + 8u * s; };      // 3
+  auto s_empty = [&](int s) { return bar_base + 88 + 8u * s; };     // 3
+  const uint32_t v_full = bar_base + 112, v_empty = bar_base + 120, p_full = bar_base + 128, p_empty = bar_base + 136,
+                 o_full = bar_base + 144, o_empty = bar_base + 152;
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem_gen + L::BAR_OFF + L::NUM_BARS * 8);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  if (warp == PRODUCER_WARP && lane == 0) {
+  if (warp == QK_PRODUCER_WARP && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
     for (int s = 0; s < 2; ++s) {
+      mbar_init(q_full(s), 1);
+      mbar_init(q_empty(s), 1);
       mbar_init(k_full(s), 1);
       mbar_init(k_empty(s), 1);
-      mbar_init(v_full(s), 1);
-      mbar_init(v_empty(s), 1);
+    }
+    for (int s = 0; s < S_BUFS; ++s) {
       mbar_init(s_full(s), 1);
       mbar_init(s_empty(s), 8);        // one arrival per softmax warp
     }
+    mbar_init(v_full, 1);
+    mbar_init(v_empty, 1);
     mbar_init(p_full, 8);
     mbar_init(p_empty, 1);
     mbar_init(o_full, 1);
@@ -128,84 +161,111 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_launch_dependents();
 
-  if (warp == PRODUCER_WARP) {
-    // ===================== TMA producer =====================
+  auto load_tile = [&](const CUtensorMap* map, uint32_t dst, int col0, int row0, uint32_t bar) {
+    mbar_expect_tx(bar, L::TILE_BYTES);
+#pragma unroll
+    for (int sl = 0; sl < L::SLABS; ++sl) tma_load_2d(dst + sl * L::SLAB_BYTES, map, col0 + sl * 64, row0, bar);
+  };
+
+  if (warp == QK_PRODUCER_WARP) {
+    // ===================== TMA producer: Q (once per item, double-buffered) and the K tile of every Q.K^T job =====================
     if (lane == 0) {
       pdl_wait();                                   // q and the cache rows come from the QKV GEMM before us
-      unsigned kcount = 0, vcount = 0, n = 0;
-      auto load_tile = [&](const CUtensorMap* map, uint32_t dst, int col0, int row0, uint32_t bar) {
-        mbar_expect_tx(bar, L::TILE_BYTES);
-#pragma unroll
-        for (int sl = 0; sl < L::SLABS; ++sl) tma_load_2d(dst + sl * L::SLAB_BYTES, map, col0 + sl * 64, row0, bar);
-      };
-      auto load_k = [&](const Item& it, int j) {
-        const int st = kcount & 1;
-        mbar_wait(k_empty(st), ((kcount >> 1) & 1) ^ 1u);
-        load_tile(&tmK, smem_base + L::K_OFF + st * L::TILE_BYTES, ((b0 + it.b) * H + it.hh) * D, j * BN, k_full(st));
-        ++kcount;
-      };
+      unsigned kcount = 0, n = 0;
       for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n) {
         const Item it = decode_item(idx, bh_count, H, nq);
-        mbar_wait(q_empty, (n & 1) ^ 1u);
-        load_tile(&tmQ, smem_base + L::Q_OFF, it.hh * D, it.b * S + it.qt * BM, q_full);
-        for (int j = 0; j < it.nblk; ++j) load_k(it, j);                 // pass 1
-        for (int j = 0; j < it.nblk; ++j) {                              // pass 2
-          load_k(it, j);
-          const int st = vcount & 1;
-          mbar_wait(v_empty(st), ((vcount >> 1) & 1) ^ 1u);
-          load_tile(&tmV, smem_base + L::V_OFF + st * L::TILE_BYTES, ((b0 + it.b) * H + it.hh) * D, j * BN, v_full(st));
-          ++vcount;
+        const int qb = n & 1;
+        mbar_wait(q_empty(qb), ((n >> 1) & 1) ^ 1u);
+        load_tile(&tmQ, smem_base + L::Q_OFF + qb * L::TILE_BYTES, it.hh * D, it.b * S + it.qt * BM, q_full(qb));
+        for (int job = 0; job < it.qk_jobs; ++job, ++kcount) {
+          const int j = job < it.nblk ? job : job - it.nblk;
+          const int st = kcount & 1;
+          mbar_wait(k_empty(st), ((kcount >> 1) & 1) ^ 1u);
+          load_tile(&tmK, smem_base + L::K_OFF + st * L::TILE_BYTES, ((b0 + it.b) * H + it.hh) * D, j * BN, k_full(st));
+        }
+      }
+    }
+  } else if (warp == V_PRODUCER_WARP) {
+    // ===================== TMA producer: the V tile of every P.V job (one stage: the next tile is not needed before the
+    // softmax of its block is through) =====================
+    if (lane == 0) {
+      pdl_wait();
+      unsigned vcount = 0;
+      for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x) {
+        const Item it = decode_item(idx, bh_count, H, nq);
+        for (int j = 0; j < it.nblk; ++j, ++vcount) {
+          mbar_wait(v_empty, (vcount & 1) ^ 1u);
+          load_tile(&tmV, smem_base + L::V_OFF, ((b0 + it.b) * H + it.hh) * D, j * BN, v_full);
         }
       }
     }
   } else if (warp == MMA_WARP) {
-    // ===================== MMA issuer =====================
+    // ===================== MMA issuer: two independent job streams served by one thread =====================
+    // Q.K^T jobs run ahead of the softmax as far as the three score buffers allow (also into the NEXT item); P.V jobs are
+    // issued the moment the softmax warps have published a P tile.  Neither stream ever blocks the other: the thread
+    // probes the barriers (mbarrier.test_wait) instead of waiting on them.
     if (lane == 0) {
       constexpr uint32_t idesc_qk = make_idesc(BM, BN);                   // A = Q (K-major), B = K (K-major)
       constexpr uint32_t idesc_pv = make_idesc(BM, D) | (1u << 16);       // A = P (K-major), B = V (MN-major)
-      unsigned kc = 0, vc = 0, sc = 0, pc = 0, n = 0;
-      auto issue_qk = [&]() {
-        const int ks = kc & 1, sb = sc & 1;
-        mbar_wait(k_full(ks), (kc >> 1) & 1);
-        mbar_wait(s_empty(sb), ((sc >> 1) & 1) ^ 1u);
-        tcgen05_fence_after();
-        const uint32_t qa = smem_base + L::Q_OFF, ka = smem_base + L::K_OFF + ks * L::TILE_BYTES;
+      int q_idx = blockIdx.x, p_idx = blockIdx.x;
+      bool q_done = q_idx >= n_items, p_done = p_idx >= n_items;
+      Item qit = decode_item(q_done ? 0 : q_idx, bh_count, H, nq), pit = qit;
+      unsigned qn = 0, pn = 0, kc = 0, sc = 0, vc = 0, pc = 0;
+      int q_job = 0, p_blk = 0;
+      while (!q_done || !p_done) {
+        bool progressed = false;
+        if (!q_done) {
+          const int ks = kc & 1, sb = sc % S_BUFS, qb = qn & 1;
+          if ((q_job > 0 || mbar_test(q_full(qb), (qn >> 1) & 1)) && mbar_test(k_full(ks), (kc >> 1) & 1) &&
+              mbar_test(s_empty(sb), ((sc / S_BUFS) & 1) ^ 1u)) {
+            tcgen05_fence_after();
+            const uint32_t qa = smem_base + L::Q_OFF + qb * L::TILE_BYTES, ka = smem_base + L::K_OFF + ks * L::TILE_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < D / 16; ++kk) {
-          const uint32_t off = (kk >> 2) * L::SLAB_BYTES + (kk & 3) * 32;   // 64-element slab, 16 elements = 32 bytes inside the swizzle row
-          tcgen05_mma_f16(tmem_base + sb * BN, make_smem_desc(qa + off), make_smem_desc(ka + off), idesc_qk, kk > 0 ? 1u : 0u);
-        }
-        tcgen05_commit(k_empty(ks));
-        tcgen05_commit(s_full(sb));
-        ++kc;
-        ++sc;
-      };
-      for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n) {
-        const Item it = decode_item(idx, bh_count, H, nq);
-        mbar_wait(q_full, n & 1);
-        for (int j = 0; j < it.nblk; ++j) issue_qk();                    // pass 1: scores only
-        issue_qk();                                                      // pass 2, block 0
-        for (int j = 0; j < it.nblk; ++j) {
-          if (j + 1 < it.nblk) issue_qk();                               // next block's scores while the softmax works on this one
-          const int vs = vc & 1;
-          mbar_wait(v_full(vs), (vc >> 1) & 1);
-          mbar_wait(p_full, pc & 1);
-          if (j == 0) mbar_wait(o_empty, (n & 1) ^ 1u);                  // the previous item's O has been read out
-          tcgen05_fence_after();
-          const uint32_t pa = smem_base + L::P_OFF, va = smem_base + L::V_OFF + vs * L::TILE_BYTES;
-#pragma unroll
-          for (int kk = 0; kk < BN / 16; ++kk) {
-            const uint64_t dp = make_smem_desc(pa + (kk >> 2) * L::SLAB_BYTES + (kk & 3) * 32);
-            const uint64_t dv = make_smem_desc_mn(va + kk * 16 * 128, L::SLAB_BYTES);   // 16 keys = 16 rows of 128 bytes
-            tcgen05_mma_f16(tmem_base + L::O_COL, dp, dv, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < D / 16; ++kk) {
+              const uint32_t off = (kk >> 2) * L::SLAB_BYTES + (kk & 3) * 32;   // 64-element slab; 16 elements = 32 bytes inside the swizzle row
+              tcgen05_mma_f16(tmem_base + sb * BN, make_smem_desc(qa + off), make_smem_desc(ka + off), idesc_qk, kk > 0 ? 1u : 0u);
+            }
+            tcgen05_commit(k_empty(ks));
+            tcgen05_commit(s_full(sb));
+            ++kc;
+            ++sc;
+            progressed = true;
+            if (++q_job == qit.qk_jobs) {
+              tcgen05_commit(q_empty(qb));            // the Q buffer is free once this item's last Q.K^T has read it
+              q_job = 0;
+              ++qn;
+              q_idx += gridDim.x;
+              if (q_idx >= n_items) q_done = true;
+              else qit = decode_item(q_idx, bh_count, H, nq);
+            }
           }
-          tcgen05_commit(v_empty(vs));
-          tcgen05_commit(p_empty);
-          ++vc;
-          ++pc;
         }
-        tcgen05_commit(o_full);
-        tcgen05_commit(q_empty);
+        if (!p_done) {
+          if (mbar_test(p_full, pc & 1) && mbar_test(v_full, vc & 1) && (p_blk > 0 || mbar_test(o_empty, (pn & 1) ^ 1u))) {
+            tcgen05_fence_after();
+            const uint32_t pa = smem_base + L::P_OFF, va = smem_base + L::V_OFF;
+#pragma unroll
+            for (int kk = 0; kk < BN / 16; ++kk) {
+              const uint64_t dp = make_smem_desc(pa + (kk >> 2) * L::SLAB_BYTES + (kk & 3) * 32);
+              const uint64_t dv = make_smem_desc_mn(va + kk * 16 * 128, L::SLAB_BYTES);   // 16 keys = 16 rows of 128 bytes
+              tcgen05_mma_f16(tmem_base + L::O_COL, dp, dv, idesc_pv, (p_blk > 0 || kk > 0) ? 1u : 0u);
+            }
+            tcgen05_commit(v_empty);
+            tcgen05_commit(p_empty);
+            ++vc;
+            ++pc;
+            progressed = true;
+            if (++p_blk == pit.nblk) {
+              tcgen05_commit(o_full);
+              p_blk = 0;
+              ++pn;
+              p_idx += gridDim.x;
+              if (p_idx >= n_items) p_done = true;
+              else pit = decode_item(p_idx, bh_count, H, nq);
+            }
+          }
+        }
+        if (!progressed) __nanosleep(20);
       }
     }
   } else {
@@ -216,95 +276,12 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const uint32_t lane_addr = (uint32_t)(wq * 32) << 16;
     float2* stat = reinterpret_cast<float2*>(smem_gen + L::STAT_OFF);
     unsigned sc = 0, pcnt = 0, n = 0;
-    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n) {
-      const Item it = decode_item(idx, bh_count, H, nq);
-      // ---------------- pass 1: m and l over this thread's 64 columns of every block
-      float m = M_INIT, l = 0.f;
-      for (int j = 0; j < it.nblk; ++j) {
-        const int sb = sc & 1;
-        mbar_wait(s_full(sb), (sc >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + lane_addr + sb * BN + g * 64;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + 32, v + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(sb));
-        ++sc;
-        const bool diag = (j == it.qt);
-        float bm = -INFINITY;
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          float s0, s1;
-          unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), s0, s1);   // s = bf16(acc): the bmm's output
-          if (diag) {
-            if (g * 64 + i > row) s0 = -INFINITY;
-            if (g * 64 + i + 1 > row) s1 = -INFINITY;
-          }
-          v[i] = __float_as_uint(s0);
-          v[i + 1] = __float_as_uint(s1);
-          bm = fmaxf(bm, fmaxf(s0, s1));
-        }
-        const float mn = fmaxf(m, bm);
-        float acc = 0.f;
-#pragma unroll
-        for (int i = 0; i < 64; ++i) acc += ex2((__uint_as_float(v[i]) - mn) * LOG2E);
-        l = l * ex2((m - mn) * LOG2E) + acc;
-        m = mn;
-      }
-      // the two column halves of a row meet: m = max, l rescaled to it
-      stat[((n & 1) * 2 + g) * BM + row] = make_float2(m, l);
-      softmax_bar_sync();
-      const float2 o2 = stat[((n & 1) * 2 + (g ^ 1)) * BM + row];
-      const float mf = fmaxf(m, o2.x);
-      const float lf = l * ex2((m - mf) * LOG2E) + o2.y * ex2((o2.x - mf) * LOG2E);
-      const float inv_l = 1.f / lf;
-      // ---------------- pass 2: p = bf16(exp(s - m) / l) -> shared memory (this half's 64 keys = one K-major slab)
-      for (int j = 0; j < it.nblk; ++j) {
-        const int sb = sc & 1;
-        mbar_wait(s_full(sb), (sc >> 1) & 1);
-        tcgen05_fence_after();
-        uint32_t v[64];
-        const uint32_t taddr = tmem_base + lane_addr + sb * BN + g * 64;
-        tmem_ld32(taddr, v);
-        tmem_ld32(taddr + 32, v + 32);
-        tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(s_empty(sb));
-        ++sc;
-        const bool diag = (j == it.qt);
-        uint32_t pk[32];
-#pragma unroll
-        for (int i = 0; i < 64; i += 2) {
-          float s0, s1;
-          unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), s0, s1);
-          float p0 = ex2((s0 - mf) * LOG2E) * inv_l;
-          float p1 = ex2((s1 - mf) * LOG2E) * inv_l;
-          if (diag) {
-            if (g * 64 + i > row) p0 = 0.f;
-            if (g * 64 + i + 1 > row) p1 = 0.f;
-          }
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-        }
-        mbar_wait(p_empty, (pcnt & 1) ^ 1u);          // the previous block's P.V has finished reading the P tile
-        const uint32_t prow = smem_base + L::P_OFF + g * L::SLAB_BYTES + row * 128;
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const uint32_t addr = prow + ((c ^ (row & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]),
-                       "r"(pk[4 * c + 3])
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-        ++pcnt;
-      }
-      // ---------------- epilogue: ctx = bf16(O), this half's d/2 columns
-      mbar_wait(o_full, n & 1);
+    Item prev{};
+    bool have_prev = false;
+
+    // ctx = bf16(O) of the item whose P.V chain the MMA thread committed as number `on`
+    auto epilogue = [&](const Item& it, unsigned on) {
+      mbar_wait(o_full, on & 1);
       tcgen05_fence_after();
       constexpr int OC = D / 2;
       uint32_t o[OC];
@@ -328,7 +305,153 @@ attn_prefill_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
           *reinterpret_cast<uint4*>(dst + 8 * c) = u;
         }
       }
+    };
+    // publish 64 probabilities (32 packed pairs) as this thread's row of the P tile's slab g
+    auto publish_p = [&](const uint32_t* pk) {
+      mbar_wait(p_empty, (pcnt & 1) ^ 1u);          // the previous block's P.V has finished reading the P tile
+      const uint32_t prow = smem_base + L::P_OFF + g * L::SLAB_BYTES + row * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const uint32_t addr = prow + ((c ^ (row & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(pk[4 * c]), "r"(pk[4 * c + 1]), "r"(pk[4 * c + 2]),
+                     "r"(pk[4 * c + 3])
+                     : "memory");
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full);
+      ++pcnt;
+    };
+
+    for (int idx = blockIdx.x; idx < n_items; idx += gridDim.x, ++n) {
+      const Item it = decode_item(idx, bh_count, H, nq);
+      const unsigned sc0 = sc;                      // first score buffer job of this item
+      // ---------------- pass 1: m and l over this thread's 64 columns of every block
+      float m = M_INIT, l = 0.f;
+      float m_blk[RESIDENT_BLOCKS];                 // resident items: the running maximum each block's exponentials refer to
+#pragma unroll
+      for (int j = 0; j < RESIDENT_BLOCKS; ++j) m_blk[j] = M_INIT;
+      for (int j = 0; j < it.nblk; ++j) {
+        const int sb = sc % S_BUFS;
+        mbar_wait(s_full(sb), (sc / S_BUFS) & 1);
+        tcgen05_fence_after();
+        uint32_t v[64];
+        const uint32_t taddr = tmem_base + lane_addr + sb * BN + g * 64;
+        tmem_ld32(taddr, v);
+        tmem_ld32(taddr + 32, v + 32);
+        tmem_ld_wait();
+        if (!it.resident) {                         // scores are recomputed in pass 2: hand the buffer back now
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty(sb));
+        }
+        ++sc;
+        float bmx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};   // four independent chains (latency, not issue, bounds this loop)
+        if (j == it.qt) {                           // diagonal block: causal mask
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float s0, s1;
+            unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), s0, s1);   // s = bf16(acc): the bmm's output
+            if (g * 64 + i > row) s0 = -INFINITY;
+            if (g * 64 + i + 1 > row) s1 = -INFINITY;
+            v[i] = __float_as_uint(s0);
+            v[i + 1] = __float_as_uint(s1);
+            bmx[(i >> 1) & 3] = fmaxf(bmx[(i >> 1) & 3], fmaxf(s0, s1));
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float s0, s1;
+            unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), s0, s1);
+            v[i] = __float_as_uint(s0);
+            v[i + 1] = __float_as_uint(s1);
+            bmx[(i >> 1) & 3] = fmaxf(bmx[(i >> 1) & 3], fmaxf(s0, s1));
+          }
+        }
+        const float mn = fmaxf(fmaxf(m, fmaxf(bmx[0], bmx[1])), fmaxf(bmx[2], bmx[3]));
+        float accx[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+          const float e = ex2((__uint_as_float(v[i]) - mn) * LOG2E);
+          accx[i & 7] += e;
+          v[i] = __float_as_uint(e);
+        }
+        l = l * ex2((m - mn) * LOG2E) + (((accx[0] + accx[1]) + (accx[2] + accx[3])) + ((accx[4] + accx[5]) + (accx[6] + accx[7])));
+        m = mn;
+        if (it.resident) {                          // keep exp(s - m_j) where the scores were: pass 2 only rescales
+          tmem_st32(taddr, v);
+          tmem_st32(taddr + 32, v + 32);
+#pragma unroll
+          for (int jj = 0; jj < RESIDENT_BLOCKS; ++jj)
+            if (jj == j) m_blk[jj] = mn;
+        }
+      }
+      if (it.resident) tmem_st_wait();
+      // the previous item's output leaves TMEM here, off the critical path (its P.V chain finished long ago)
+      if (have_prev) epilogue(prev, n - 1);
+      // the two column halves of a row meet: m = max, l rescaled to it
+      stat[((n & 1) * 2 + g) * BM + row] = make_float2(m, l);
+      pair_bar_sync(wq);
+      const float2 o2 = stat[((n & 1) * 2 + (g ^ 1)) * BM + row];
+      const float mf = fmaxf(m, o2.x);
+      const float lf = l * ex2((m - mf) * LOG2E) + o2.y * ex2((o2.x - mf) * LOG2E);
+      const float inv_l = 1.f / lf;
+      // ---------------- pass 2: p = bf16(exp(s - m) / l) -> shared memory (this half's 64 keys = one K-major slab)
+      if (it.resident) {
+#pragma unroll
+        for (int j = 0; j < RESIDENT_BLOCKS; ++j) {
+          if (j < it.nblk) {
+            const int sb = (sc0 + j) % S_BUFS;
+            const uint32_t taddr = tmem_base + lane_addr + sb * BN + g * 64;
+            uint32_t v[64];
+            tmem_ld32(taddr, v);
+            tmem_ld32(taddr + 32, v + 32);
+            tmem_ld_wait();
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(s_empty(sb));
+            const float f = ex2((m_blk[j] - mf) * LOG2E) * inv_l;
+            uint32_t pk[32];
+#pragma unroll
+            for (int i = 0; i < 64; i += 2) pk[i >> 1] = pack_bf16x2(__uint_as_float(v[i]) * f, __uint_as_float(v[i + 1]) * f);
+            publish_p(pk);
+          }
+        }
+      } else {
+        for (int j = 0; j < it.nblk; ++j) {
+          const int sb = sc % S_BUFS;
+          mbar_wait(s_full(sb), (sc / S_BUFS) & 1);
+          tcgen05_fence_after();
+          uint32_t v[64];
+          const uint32_t taddr = tmem_base + lane_addr + sb * BN + g * 64;
+          tmem_ld32(taddr, v);
+          tmem_ld32(taddr + 32, v + 32);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(s_empty(sb));
+          ++sc;
+          const bool diag = (j == it.qt);
+          uint32_t pk[32];
+#pragma unroll
+          for (int i = 0; i < 64; i += 2) {
+            float s0, s1;
+            unpack_bf16x2(pack_bf16x2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), s0, s1);
+            float p0 = ex2((s0 - mf) * LOG2E) * inv_l;
+            float p1 = ex2((s1 - mf) * LOG2E) * inv_l;
+            if (diag) {
+              if (g * 64 + i > row) p0 = 0.f;
+              if (g * 64 + i + 1 > row) p1 = 0.f;
+            }
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+          }
+          publish_p(pk);
+        }
+      }
+      prev = it;
+      have_prev = true;
     }
+    if (have_prev) epilogue(prev, n - 1);
   }
 
   tcgen05_fence_before();
