@@ -251,8 +251,11 @@ def parity_check(m, cfg, args, st, ids_dev, out_tokens, rank, world, dev):
     B, S, new = args.batch_size, args.input_tokens, args.max_new_tokens
     if dec.layout.dp != dec.layout.d:
         return {"skipped": "head-padded layout: oracle weights are not views of the slabs"}
-    torch.cuda.empty_cache()
-    free = torch.cuda.mem_get_info(dev)[0]
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
+        free = torch.cuda.mem_get_info(dev)[0]
+    else:
+        free = 1 << 42
     Wl = 2.0 * (12 * h * h + 13 * h)
     cache_bytes = L * 4.0 * (S + new) * B * h
     scratch = 6.0 * B * S * max(f, S * cfg.num_attention_heads) * 2 + (8 << 30)
@@ -344,7 +347,8 @@ def parity_check(m, cfg, args, st, ids_dev, out_tokens, rank, world, dev):
                        "it count; every first divergence is classified by the oracle's own top-2 margin there (<= 2 ulp = a tie "
                        "that fp32 summation order decides)")
     del cache, layers, om
-    torch.cuda.empty_cache()
+    if dev.type == "cuda":
+        torch.cuda.empty_cache()
     return res
 
 
@@ -449,7 +453,8 @@ def _main(args, json_out):
             parity = parity_check(m, cfg, args, st, ids_dev, out, rank, world, dev)
         except torch.OutOfMemoryError as e:      # the checker must never cost the line its throughput numbers
             parity = {"skipped": f"oracle ran out of memory: {str(e)[:120]}"}
-            torch.cuda.empty_cache()
+            if dev.type == "cuda":
+                torch.cuda.empty_cache()
         tp.barrier()
 
     # ---- roofline of the dominant kernel: instrument one prefill pass, CUDA events around every GEMM launch

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define LIA_ABI_VERSION 3
+#define LIA_ABI_VERSION 4
 
 typedef void* lia_stream_t; /* cudaStream_t */
 
@@ -213,6 +213,37 @@ int lia_streamer_release(LiaStreamer* s, int slot, lia_stream_t compute_stream);
 /* total bytes copied and device-measured copy milliseconds since creation (blocks on the copy stream). */
 int lia_streamer_stats(LiaStreamer* s, double* bytes, double* copy_ms);
 int lia_streamer_destroy(LiaStreamer* s);
+
+/* ---- decode programs: a chain of decode-shaped operations (at most 128 token rows each) executed as ONE persistent
+ * kernel -- what a decode step of the reference spends ~30 library launches per layer on (lia/modeling_opt.py:1379-1491
+ * driving decoder.py:172-335 and attentions.py:312-557; models.py:423-431 and greedy_search.py:367-395 for the head).
+ * Operations run in the order they were added; each starts when all earlier ones are complete on every SM, while the
+ * weight tiles of later GEMMs and the cached K/V rows of later attention operations already stream into shared memory.
+ * Every operation computes exactly what its stand-alone entry point computes (same kernels' code, same summation order):
+ * results are bit-identical to calling lia_layernorm_bf16 / lia_gemm_bf16 / lia_gemm_allreduce_bf16 /
+ * lia_attn_decode_bf16 (splits == 1) / lia_embed_masked_bf16 / lia_argmax_bf16 one after the other.
+ * All pointers are device pointers owned by the caller and must stay valid until lia_program_destroy. */
+typedef struct LiaProgram LiaProgram;
+LiaProgram* lia_program_create(int rows);                       /* rows = token rows (1..128) of every operation */
+int lia_program_add_layernorm(LiaProgram* p, const void* x, const void* w, const void* b, void* y, int rows, int h, float eps);
+/* as lia_gemm_bf16 (tp == NULL) or lia_gemm_allreduce_bf16 (tp != NULL; `epilogue` ignored).  A LIA_EPI_QKV
+ * epilogue appends at the position given to lia_program_run (qkv->pos0 is ignored). */
+int lia_program_add_gemm(LiaProgram* p, const void* A, const void* W, const void* bias, const void* residual, void* out, int M,
+                         int N, int K, int epilogue, const LiaQkvArgs* qkv, const LiaTpArgs* tp);
+/* as lia_attn_decode_bf16 with T = pos0 + 1 of the run; cache_rows = rows the cache tensors have */
+int lia_program_add_attn_decode(LiaProgram* p, const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H,
+                                int d, int cache_batch, int b0, int cache_rows);
+/* as lia_embed_masked_bf16 with S = 1, past_len = pos0 and ids = the run's ids_in */
+int lia_program_add_embed(LiaProgram* p, const int64_t* attention_mask, int mask_ld, const void* embed_tokens,
+                          const void* embed_positions, void* out, int B, int h, int vocab, int max_pos_rows);
+/* as lia_argmax_bf16 into the run's ids_out, with the run's suppress_id */
+int lia_program_add_argmax(LiaProgram* p, const void* logits, int B, int V);
+int lia_program_finalize(LiaProgram* p);                        /* uploads the program; no more operations after it */
+/* one launch: pos0 = positions already cached (the new token is appended at pos0 and attends to pos0 + 1 keys) */
+int lia_program_run(LiaProgram* p, int pos0, const int64_t* ids_in, int64_t* ids_out, int suppress_id, lia_stream_t stream);
+int lia_program_error(LiaProgram* p);                           /* 0 = ok, 1 = a CTA timed out; synchronises the device */
+int lia_program_num_ops(LiaProgram* p);
+int lia_program_destroy(LiaProgram* p);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libliab200.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV = 0, 1, 2, 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 TP_MAX_WORLD = 8
 P2P_HANDLE_BYTES = 64
 
@@ -71,6 +71,18 @@ _PROTOTYPES = {
     "lia_streamer_release": (c_int, [c_void_p, c_int, c_void_p]),
     "lia_streamer_stats": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double)]),
     "lia_streamer_destroy": (c_int, [c_void_p]),
+    "lia_program_create": (c_void_p, [c_int]),
+    "lia_program_add_layernorm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_float]),
+    "lia_program_add_gemm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                     POINTER(LiaQkvArgs), POINTER(LiaTpArgs)]),
+    "lia_program_add_attn_decode": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "lia_program_add_embed": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "lia_program_add_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int]),
+    "lia_program_finalize": (c_int, [c_void_p]),
+    "lia_program_run": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p]),
+    "lia_program_error": (c_int, [c_void_p]),
+    "lia_program_num_ops": (c_int, [c_void_p]),
+    "lia_program_destroy": (c_int, [c_void_p]),
 }
 
 EXPORTS = tuple(_PROTOTYPES)

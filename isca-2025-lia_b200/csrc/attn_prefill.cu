@@ -174,7 +174,6 @@ __global__ void __launch_bounds__(THREADS) attn_prefill_kernel(const bf16* __res
   }
   const float mm0 = m0 > -INFINITY ? m0 : 0.f, mm1 = m1 > -INFINITY ? m1 : 0.f;
   const float ll0 = l0 > 0.f ? l0 : 1.f, ll1 = l1 > 0.f ? l1 : 1.f;
-  const float il0 = 1.f / ll0, il1 = 1.f / ll1;
 
   // ---------------- pass 2: p = bf16(exp(s-m)/l), O += p.v
   float o[D / 8][4];

@@ -51,3 +51,4 @@ extern "C" int lia_device_info(int* sm_count, int* cc_major, int* cc_minor) {
   }
   return LIA_OK;
 }
+

@@ -102,6 +102,15 @@ __device__ __forceinline__ uint4 ldg_stream(const void* p) {
   return r;
 }
 
+// 128-bit load of ACTIVATIONS: cached in L2 only, so it always sees what other SMs have written -- also data produced
+// earlier in the SAME launch (the decode program kernel chains operations inside one grid; a non-coherent .nc load could
+// return a stale L1 line there).  Costs the same as ldg_stream: neither allocates in L1.
+__device__ __forceinline__ uint4 ldg_act(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

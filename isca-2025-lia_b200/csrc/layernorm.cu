@@ -7,6 +7,7 @@
 // (h <= 2048) or by one 128-thread CTA (h <= 16384), so reductions are warp shuffles plus at
 // most one shared-memory hop.
 #include "common.cuh"
+#include "small_ops.cuh"
 
 namespace {
 
@@ -17,70 +18,8 @@ __global__ void __launch_bounds__(128) layernorm_kernel(const bf16* __restrict__
   pdl_launch_dependents();
   pdl_wait();
   constexpr int ROWS_PER_CTA = 128 / TPR;
-  __shared__ float red[2][4];
-  const int row = blockIdx.x * ROWS_PER_CTA + threadIdx.x / TPR;
-  const int t = threadIdx.x % TPR;
-  const int nvec = h >> 3;
-  const bool active = row < rows;
-  const bf16* xr = x + (size_t)row * h;
-
-  uint4 v[VMAX];
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < VMAX; ++i) {
-    const int idx = t + i * TPR;
-    if (active && idx < nvec) {
-      v[i] = ldg_stream(xr + idx * 8);
-      float f[8];
-      unpack8(v[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) sum += f[j];
-    }
-  }
-  sum = warp_sum(sum);
-  if (TPR > 32) {
-    if ((threadIdx.x & 31) == 0) red[0][threadIdx.x >> 5] = sum;
-    __syncthreads();
-    sum = red[0][0] + red[0][1] + red[0][2] + red[0][3];
-  }
-  const float mean = sum / (float)h;
-
-  float sq = 0.f;
-#pragma unroll
-  for (int i = 0; i < VMAX; ++i) {
-    const int idx = t + i * TPR;
-    if (active && idx < nvec) {
-      float f[8];
-      unpack8(v[i], f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float dlt = f[j] - mean;
-        sq += dlt * dlt;
-      }
-    }
-  }
-  sq = warp_sum(sq);
-  if (TPR > 32) {
-    if ((threadIdx.x & 31) == 0) red[1][threadIdx.x >> 5] = sq;
-    __syncthreads();
-    sq = red[1][0] + red[1][1] + red[1][2] + red[1][3];
-  }
-  const float rstd = rsqrtf(sq / (float)h + eps);
-
-  bf16* yr = y + (size_t)row * h;
-#pragma unroll
-  for (int i = 0; i < VMAX; ++i) {
-    const int idx = t + i * TPR;
-    if (active && idx < nvec) {
-      float f[8], g[8], bb[8];
-      unpack8(v[i], f);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(w + idx * 8)), g);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(b + idx * 8)), bb);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = (f[j] - mean) * rstd * g[j] + bb[j];
-      *reinterpret_cast<uint4*>(yr + idx * 8) = pack8(f);
-    }
-  }
+  __shared__ float red[8];
+  layernorm_rows<TPR, VMAX>(x, w, b, y, rows, h, eps, blockIdx.x * ROWS_PER_CTA, threadIdx.x, red, [] { __syncthreads(); });
 }
 
 }  // namespace

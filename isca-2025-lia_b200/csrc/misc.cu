@@ -1,6 +1,7 @@
 // Small HBM-bound kernels either side of the layer stack: embeddings, greedy argmax,
 // residual add after a tensor-parallel all-reduce.
 #include "common.cuh"
+#include "small_ops.cuh"
 
 namespace {
 
@@ -15,42 +16,8 @@ __global__ void __launch_bounds__(128) embed_kernel(const int64_t* __restrict__ 
                                                     const int64_t* __restrict__ mask, int mask_ld) {
   pdl_launch_dependents();
   pdl_wait();
-  const int row = blockIdx.x;          // b*S + s
-  const int s = row % S;
-  long long id = ids[row];
-  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
-  long long p = past_len + s;
-  if (mask != nullptr) {
-    __shared__ long long part[4];
-    const int64_t* mr = mask + (size_t)(row / S) * mask_ld;
-    const int t = past_len + s;
-    long long c = 0;
-    for (int j = threadIdx.x; j <= t; j += 128) c += mr[j];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = c;
-    __syncthreads();
-    p = (part[0] + part[1] + part[2] + part[3]) * mr[t] - 1;
-  }
-  p += 2;
-  p = p < 0 ? 0 : (p >= max_pos_rows ? max_pos_rows - 1 : p);
-  // a null table contributes nothing: the row of the other table is copied through unchanged (opt-350m looks its
-  // token rows [e] and position rows [h] up separately; they meet in project_in's residual epilogue, M:1139-1142)
-  const bf16* tr = tok != nullptr ? tok + (size_t)id * h : nullptr;
-  const bf16* pr = pos != nullptr ? pos + (size_t)p * h : nullptr;
-  bf16* o = out + (size_t)row * h;
-  for (int i = threadIdx.x * 8; i < h; i += 128 * 8) {
-    if (tr != nullptr && pr != nullptr) {
-      float a[8], c[8];
-      unpack8(__ldg(reinterpret_cast<const uint4*>(tr + i)), a);
-      unpack8(__ldg(reinterpret_cast<const uint4*>(pr + i)), c);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] += c[j];
-      *reinterpret_cast<uint4*>(o + i) = pack8(a);
-    } else {
-      *reinterpret_cast<uint4*>(o + i) = __ldg(reinterpret_cast<const uint4*>((tr != nullptr ? tr : pr) + i));
-    }
-  }
+  __shared__ long long part[4];
+  embed_row(ids, tok, pos, out, blockIdx.x, S, h, past_len, vocab, max_pos_rows, mask, mask_ld, threadIdx.x, part, [] { __syncthreads(); });
 }
 
 // next[b] = argmax_v logits[b,v], lowest index on ties, one id optionally suppressed
@@ -61,52 +28,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const bf16* __restrict__ lo
   pdl_wait();
   __shared__ float sv[8];
   __shared__ int si[8];
-  const bf16* row = logits + (size_t)blockIdx.x * V;
-  float best = -INFINITY;
-  int bi = 0x7fffffff;
-  const int nvec = V >> 3;
-  for (int i = threadIdx.x; i < nvec; i += 256) {
-    float f[8];
-    unpack8(ldg_stream(row + i * 8), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int idx = i * 8 + j;
-      const float v = (idx == suppress) ? -INFINITY : f[j];
-      if (v > best || (v == best && idx < bi)) {
-        best = v;
-        bi = idx;
-      }
-    }
-  }
-  for (int idx = nvec * 8 + threadIdx.x; idx < V; idx += 256) {
-    const float v = (idx == suppress) ? -INFINITY : __bfloat162float(row[idx]);
-    if (v > best || (v == best && idx < bi)) {
-      best = v;
-      bi = idx;
-    }
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ov > best || (ov == best && oi < bi)) {
-      best = ov;
-      bi = oi;
-    }
-  }
-  if ((threadIdx.x & 31) == 0) {
-    sv[threadIdx.x >> 5] = best;
-    si[threadIdx.x >> 5] = bi;
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int w = 1; w < 8; ++w)
-      if (sv[w] > best || (sv[w] == best && si[w] < bi)) {
-        best = sv[w];
-        bi = si[w];
-      }
-    next[blockIdx.x] = (bi == 0x7fffffff) ? 0 : bi;
-  }
+  argmax_row<256>(logits + (size_t)blockIdx.x * V, next + blockIdx.x, V, suppress, threadIdx.x, sv, si, [] { __syncthreads(); });
 }
 
 // out = bf16(residual + x): the residual add that follows the all-reduce of a row-parallel

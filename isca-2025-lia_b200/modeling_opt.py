@@ -30,7 +30,7 @@ from dataclasses import dataclass, field
 
 import torch
 
-from . import _lib, graphs, ops, tp as tp_mod
+from . import _lib, graphs, ops, program as program_mod, tp as tp_mod
 from .ops import EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV
 from .kv_spill import KVSpill, plan_resident_layers
 from .streamer import HostArena, LayerStreamer
@@ -169,6 +169,7 @@ class _GenState:
         self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.ws = _Workspace(cfg, model.layout, rows, B, dev, self.arena)
         self.graphs = {}
+        self.program = None         # program.DecodeProgram: the whole decode step as one persistent kernel (False: unsupported)
         self.calls = 0
         # KV cache last, once everything else of this shape is placed: layers whose K/V do not fit in HBM are
         # spilled to pinned host memory (kv_spill.py; lia/modeling_opt.py:326-349 keeps the whole cache there)
@@ -198,6 +199,10 @@ class _GenState:
         return tuple((marker, k, v, self.beam_idx) for k, v in zip(ks, vs))
 
     def close(self):
+        if self.program:
+            self.program.close()
+        self.program = None
+        self.graphs = {}
         if self.arena is not None:
             self.arena.close()
             self.arena = None
@@ -278,6 +283,8 @@ class OPTDecoder:
         self.host_slabs = []
         self.streamer = None
         self._ws = {}
+        self.k = ops                # kernel layer the compute methods call: lia_b200.ops, or a program.ProgramRecorder while a
+                                    # decode program is being built from the very same methods
 
     # ---- weights & placement (move_gpu_layer / pin_memory, lia/modeling_opt.py:167-268)
     def load_layers(self, layer_fn, gpu_percentage=100):
@@ -362,21 +369,21 @@ class OPTDecoder:
     def embed_rows(self, ids, past_len, mask, out, ws):
         """hidden = project_in(embed_tokens[ids]) + embed_positions[pos]  (M:1107-1142) into ``out`` [B,S,h]."""
         if self.project_in is None:
-            return ops.embed(ids, self.embed_tokens, self.embed_positions, past_len, out=out, attention_mask=mask)
+            return self.k.embed(ids, self.embed_tokens, self.embed_positions, past_len, out=out, attention_mask=mask)
         B, S = ids.shape
         h, ed = self.config.hidden_size, self.config.embed_dim
-        tok = ops.embed(ids, self.embed_tokens, None, past_len, attention_mask=mask)      # token rows [B,S,e] (no table = +0)
-        pos = ops.embed(ids, None, self.embed_positions, past_len, attention_mask=mask)   # position rows [B,S,h]
-        ops.gemm(tok.view(B * S, ed), self.project_in, None, out=out.view(B * S, h), epilogue=EPI_BIAS_RESIDUAL,
+        tok = self.k.embed(ids, self.embed_tokens, None, past_len, attention_mask=mask)      # token rows [B,S,e] (no table = +0)
+        pos = self.k.embed(ids, None, self.embed_positions, past_len, attention_mask=mask)   # position rows [B,S,h]
+        self.k.gemm(tok.view(B * S, ed), self.project_in, None, out=out.view(B * S, h), epilogue=EPI_BIAS_RESIDUAL,
                  residual=pos.view(B * S, h), workspace=ws.gemm)                                   # M:1139-1142
         return out
 
     def final_rows(self, rows, ws, out=None):
         """Final LayerNorm (pre-LN models, M:1563-1564) and project_out (M:1566-1567) over ``rows`` [M,h]."""
         if self.final_ln_w is not None:
-            rows = ops.layernorm(rows, self.final_ln_w, self.final_ln_b, LN_EPS, out=out)
+            rows = self.k.layernorm(rows, self.final_ln_w, self.final_ln_b, LN_EPS, out=out)
         if self.project_out is not None:
-            rows = ops.gemm(rows, self.project_out, None, epilogue=EPI_BIAS, workspace=ws.gemm)
+            rows = self.k.gemm(rows, self.project_out, None, epilogue=EPI_BIAS, workspace=ws.gemm)
         return rows
 
     def check_gpu_percentage(self, gpu_percentage):
@@ -404,15 +411,15 @@ class OPTDecoder:
         """out = residual + (a . w^T + b), summed over the tensor-parallel ranks (out_proj D:222-247, fc2 D:302-317)."""
         arena = ws.arena
         if self.tp_world == 1:
-            ops.gemm(a, w, b, out=out, epilogue=EPI_BIAS_RESIDUAL, residual=residual, workspace=ws.gemm)   # D:228-229, 309-310
+            self.k.gemm(a, w, b, out=out, epilogue=EPI_BIAS_RESIDUAL, residual=residual, workspace=ws.gemm)   # D:228-229, 309-310
         elif arena is not None:             # D:60-68 + 247/317 as one kernel over NVLink peer memory
             # prefill tiles are finished by their owner rank, which writes `out` remotely: it must live in the arena
-            ops.gemm_allreduce(a, w, b, residual, out, arena.args(out if big else None), workspace=ws.gemm)
+            self.k.gemm_allreduce(a, w, b, residual, out, arena.args(out if big else None), workspace=ws.gemm)
         else:
             part = ws.tp[:a.shape[0]]
-            ops.gemm(a, w, b, out=part, epilogue=EPI_BIAS, workspace=ws.gemm)                              # D:60-68
+            self.k.gemm(a, w, b, out=part, epilogue=EPI_BIAS, workspace=ws.gemm)                              # D:60-68
             tp_mod.all_reduce(part)
-            ops.residual_add(part, residual, out=out)                                                      # D:247, 317
+            self.k.residual_add(part, residual, out=out)                                                      # D:247, 317
 
     def layer_rows(self, v, rows, kc, vc, nb, S, pos0, b0, ws):
         M = nb * S
@@ -423,24 +430,24 @@ class OPTDecoder:
         x1 = ws.x1d[:M] if S == 1 else ws.x1[:M]
         pre = self.pre_ln
         if pre:
-            ops.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                               # decoder.py:198-204
-        ops.gemm(ln if pre else rows, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                       # attentions.py:376-491
-                 qkv=ops.qkv_args(q, kc, vc, S, pos0, b0, self.scaling), workspace=ws.gemm)
+            self.k.layernorm(rows, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                               # decoder.py:198-204
+        self.k.gemm(ln if pre else rows, v["qkv_w"], v["qkv_b"], epilogue=EPI_QKV,                       # attentions.py:376-491
+                 qkv=self.k.qkv_args(q, kc, vc, S, pos0, b0, self.scaling), workspace=ws.gemm)
         if S != 1:
-            ops.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
+            self.k.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
         else:
-            ops.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
+            self.k.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
         self._row_parallel(ctx, v["o_w"], v["o_b"], rows, x1, ws, big)                                # decoder.py:222-247
         if pre:
-            ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                 # decoder.py:266-272
-            ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
+            self.k.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                 # decoder.py:266-272
+            self.k.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
             self._row_parallel(ffn, v["fc2_w"], v["fc2_b"], x1, rows, ws, big)                        # decoder.py:302-317
         else:
             # opt-350m: LayerNorm follows each residual add; its output is both the MLP input and the next residual
-            ops.layernorm(x1, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                 # decoder.py:250-256
-            ops.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
+            self.k.layernorm(x1, v["ln1_w"], v["ln1_b"], LN_EPS, out=ln)                                 # decoder.py:250-256
+            self.k.gemm(ln, v["fc1_w"], v["fc1_b"], out=ffn, epilogue=EPI_BIAS_RELU, workspace=ws.gemm)  # decoder.py:285
             self._row_parallel(ffn, v["fc2_w"], v["fc2_b"], ln, x1, ws, big)                          # decoder.py:302-317
-            ops.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=rows)                               # decoder.py:320-321
+            self.k.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=rows)                               # decoder.py:320-321
 
     def set_overlap(self, overlap, spill=None):
         """``--no-overlap`` (M:1173): transfers of streamed layers / spilled K/V are not fetched ahead but serialised
@@ -617,7 +624,7 @@ class OPTForCausalLM:
         """Tied lm_head (lia/modeling_opt.py:1660), no bias: one GEMM against embed_tokens."""
         dec = self.model.decoder
         ws = ws or dec.workspace(rows.shape[0], rows.shape[0])
-        return ops.gemm(rows, dec.embed_tokens, None, out=out, epilogue=EPI_BIAS, workspace=ws.gemm)
+        return dec.k.gemm(rows, dec.embed_tokens, None, out=out, epilogue=EPI_BIAS, workspace=ws.gemm)
 
     # ---- generation
     def _state(self, B, S, new, num_minibatch):
@@ -633,7 +640,7 @@ class OPTForCausalLM:
         dec = self.model.decoder
         xn = dec.final_rows(rows, st.ws, out=st.xn)                                       # M:1563-1567 (last position)
         self.lm_head(xn, out=st.logits, ws=st.ws)                                         # models.py:431
-        ops.argmax(st.logits, suppress, out=st.steps_tok[t])                              # greedy_search.py:367-395
+        self.model.decoder.k.argmax(st.logits, suppress, out=st.steps_tok[t])                              # greedy_search.py:367-395
 
     def _prefill(self, st, num_minibatch, suppress):
         dec, cfg = self.model.decoder, self.config
@@ -650,6 +657,30 @@ class OPTForCausalLM:
         dec.embed_rows(st.steps_tok[t - 1].view(st.B, 1), past, st.mask, st.xd.view(st.B, 1, cfg.hidden_size), st.ws)
         dec.run_layers(st.xd, st.kc, st.vc, st.B, 1, past, 1, st.ws, st.spill)
         self._head_and_pick(st, st.xd, t, suppress)
+
+    def _decode_program(self, st):
+        """The decode step of this generation shape as ONE persistent kernel (program.py, csrc/decode_program_sm100.cu),
+        built by running ``_decode_step`` once against a recorder instead of the kernel layer.  None when the step cannot be
+        a program (not asked for with LIA_DECODE_PROGRAM=1 -- the CUDA-graph replay of the kernel-per-operation step is the
+        faster of the two today, profiles/README.md --, more than 128 sequences, a host-side collective in the step, too many cached
+        positions for the score buffer): the caller then replays CUDA graphs of the kernel-per-operation step."""
+        if st.program is None:
+            st.program = False
+            if os.environ.get("LIA_DECODE_PROGRAM", "0") != "0" and st.B <= 128 and st.new > 1 and self.device.type == "cuda":
+                dec = self.model.decoder
+                prog = None
+                try:
+                    prog = program_mod.DecodeProgram(st.B)
+                    dec.k = program_mod.ProgramRecorder(prog, self.device)
+                    self._decode_step(st, 1, -1)
+                    prog.finalize()
+                    st.program = prog
+                except program_mod.ProgramUnsupported:
+                    if prog is not None:
+                        prog.close()
+                finally:
+                    dec.k = ops
+        return st.program or None
 
     def generate(self, input_ids, max_new_tokens=32, min_new_tokens=None, do_sample=False, num_beams=1,
                  temperature=None, attention_mask=None, prefill_policy=None, decoding_policy=None, no_overlap=None,
@@ -693,9 +724,13 @@ class OPTForCausalLM:
         ev[0].record()
         self._prefill(st, num_minibatch, eos if 0 < min_new else -1)
         ev[1].record()
+        prog = self._decode_program(st) if graphs_ok else None
         for t in range(1, new):
             suppress = eos if t < min_new else -1
-            if graphs_ok and st.calls >= 2:
+            if prog is not None:
+                # one persistent kernel per step: embedding, every layer, final LayerNorm, lm_head and argmax
+                prog.run(st.S + t - 1, st.steps_tok[t - 1], st.steps_tok[t], suppress)
+            elif graphs_ok and st.calls >= 2:
                 g = st.graphs.get((t, suppress))
                 if g is None:
                     g = torch.cuda.CUDAGraph()
@@ -711,6 +746,8 @@ class OPTForCausalLM:
         torch.cuda.synchronize(self.device)
         if st.arena is not None and os.environ.get("LIA_TP_SELF_LOOP", "0") == "0":
             st.arena.check()                          # a peer that never showed up: raise instead of returning garbage
+        if prog is not None:
+            prog.check()                              # a CTA that timed out on a dependency: raise, do not return garbage
         lat = [ev[i].elapsed_time(ev[i + 1]) / 1e3 for i in range(new)]
         self.last_timing = {"prefill_s": lat[0], "decode_s": lat[1:], "total_s": sum(lat)}
         if self.config.token_latency:

@@ -37,7 +37,7 @@ def test_header_symbols_exported_and_bound(built):
 
 def test_abi_version_and_struct_layout(built):
     lib = built.load()
-    assert lib.lia_abi_version() == built.ABI_VERSION == 3
+    assert lib.lia_abi_version() == built.ABI_VERSION == 4
     # LiaQkvArgs: 3 pointers + 5 int32 + 1 float, natural alignment
     assert ctypes.sizeof(built.LiaQkvArgs) == 48
     assert built.LiaQkvArgs.hq.offset == 24 and built.LiaQkvArgs.q_scale.offset == 44

@@ -329,6 +329,11 @@ def test_bench_line_contract_dry_run(cpu_ops, monkeypatch):
     assert r["bound"] == "tensor" and r["unit"] == "TFLOP/s" and r["launches"] == 4 * 2 * 2       # 4 GEMMs x 2 layers x 2 minibatches
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
     assert line["roofline_decode"]["bound"] == "hbm" and "workload" in line["config"] and "model" not in line["config"]
+    # the parity block compares the timed model's own outputs with the oracle; on the kernel stand-in (same PyTorch ops, one
+    # thread) the two are the same arithmetic, so the comparison must come out exact
+    par = line["parity"]
+    assert par["prefill_hidden_rel_err"] == 0.0 and par["tokens_equal_frac"] == 1.0 and par["sequences_identical"] == 4
+    assert par["first_divergences"] == 0 and par["tokens_compared"] == 4 * 4
 
 
 # ------------------------------------------------------------------ placement knobs end to end: streamed layers, spilled K/V
