@@ -448,7 +448,9 @@ def _main(args, json_out):
 
     # ---- parity of the timed result (outside the timed region; st.x still holds the last prefill's hidden states)
     parity = None
-    if not args.no_parity:
+    if args.weights == "dummy":
+        parity = {"skipped": "dummy U[0,1) weights (utils/opt-weight-gen.py:61-62) overflow bf16 within a layer: throughput-only workload"}
+    elif not args.no_parity:
         try:
             parity = parity_check(m, cfg, args, st, ids_dev, out, rank, world, dev)
         except torch.OutOfMemoryError as e:      # the checker must never cost the line its throughput numbers

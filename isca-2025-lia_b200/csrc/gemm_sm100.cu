@@ -325,8 +325,36 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       if (!SWAP) {
         // tile rows = tokens (TMEM lanes), columns = output features
         const uint32_t stg = smem_base + STAGES * L::STAGE_BYTES + ew * 4096;
+        // Everything a 64-column slab's stores need besides the accumulator -- the bias chunk of this thread's 8 columns and
+        // the residual chunks of its 8 rows -- is requested ONE SLAB AHEAD: 8 independent 16-byte loads per thread in flight
+        // under the previous slab's TMEM read, transposition and stores.  (Fetched one by one inside the store loop, every
+        // store waited out a full L2 round trip: the K = h/8 row-parallel projections of a TP8 prefill ran 4x slower than
+        // their MMAs.)
+        const int ch_s = lane & 7;
+        const bool want_res = !tp_on && p.mode == LIA_EPI_BIAS_RESIDUAL;
+        float bias_s[8], bias_nx[8];
+        uint4 res_s[8], res_nx[8];
+        auto slab_fetch = [&](int c0f, float* bo, uint4* ro) {
+          const int n_f = w.tb * BN + c0f + ch_s * 8;
+          const bool ok = c0f < BN && n_f < p.N && (BN % 64 == 0 || c0f + ch_s * 8 < BN);
+          if (ok) epilogue_load_bias8(p, n_f, bo);
+          if (want_res) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int m_f = (w.ta * row_tile + (int)cta_rank) * TILE_A + ew * 32 + it * 4 + (lane >> 3);
+              ro[it] = (ok && m_f < p.M) ? ldg_act(p.residual + (size_t)m_f * p.N + n_f) : make_uint4(0, 0, 0, 0);
+            }
+          }
+        };
+        slab_fetch(0, bias_nx, res_nx);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 64) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            bias_s[i] = bias_nx[i];
+            res_s[i] = res_nx[i];
+          }
+          slab_fetch(c0 + 64, bias_nx, res_nx);           // the next slab's operands travel while this one is processed
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             if (BN % 64 != 0 && c0 + half * 32 >= BN) continue;   // (compile-time false for 128/256-wide tiles)
@@ -370,17 +398,15 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
               if (tp_on) {
                 // partial tile (r2 = bf16(bf16(acc) + bias/world)) -> the owner's receive area, slot [tile][this rank]
                 if (p.bias != nullptr) {
-                  float b[8];
-                  epilogue_load_bias8(p, n, b);
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i] + b[i]);
+                  for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i] + bias_s[i]);
                 }
                 const int u = w.ta * tiles_b + w.tb;
                 bf16* dst = tp.recv(u % tp.world, parity) + ((size_t)(u / tp.world) * tp.world + tp.rank) * (TILE_A * BN) +
                             (size_t)(ew * 32 + r) * BN + c0 + ch * 8;
                 *reinterpret_cast<uint4*>(dst) = pack8(f);
               } else {
-                epilogue_store8(p, m, n, f);
+                epilogue_finish8(p, m, n, f, bias_s, res_s[it]);
               }
             }
           }
