@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="PCIe-bound configs whose single generate() takes minutes (c3, c5a): ONE warm-up pass instead of >= 3 and no "
+                         "second (host-buffer) timed pass; the line says so -- never use it for the headline config")
     a = ap.parse_args()
     preset = CONFIGS[a.config or "c2"]
     explicit = {k: getattr(a, k) for k in preset if getattr(a, k) is not None}
@@ -290,11 +293,26 @@ def parity_check(m, cfg, args, st, ids_dev, out_tokens, rank, world, dev):
           "embed_positions": dec.embed_positions, "final_ln_w": dec.final_ln_w, "final_ln_b": dec.final_ln_b,
           "project_in": dec.project_in, "project_out": dec.project_out}
 
-    class Last:      # keeps only the last layer's hidden state (48 x 235 MB otherwise)
-        def __init__(self):
-            self.x, self.n = None, 0
+    mb = max(1, B // max(1, args.num_minibatch))
+    per_layer = world == 1 and dec.n_resident == L and dev.type == "cuda"
+
+    class Last:
+        """Receives every layer's hidden state from the oracle; keeps only the last one (48 x 235 MB otherwise).  At one GPU it
+        also runs THIS build's layer on the oracle's own input of that layer (first minibatch) -- the north-star criterion is a
+        per-layer error, which a chained comparison over 48 layers cannot show (rounding noise accumulates like a random walk)."""
+
+        def __init__(self, x0):
+            self.x, self.n, self.errs = x0, 0, []
 
         def append(self, x):
+            if per_layer:
+                H_, d_ = cfg.num_attention_heads, h // cfg.num_attention_heads
+                rows = self.x[:mb].reshape(mb * S, h).clone()
+                kc = torch.zeros(S, mb, H_, d_, dtype=torch.bfloat16, device=dev)
+                vc = torch.zeros_like(kc)
+                dec.layer_rows(dec.resident_views[self.n], rows, kc, vc, mb, S, 0, 0, st.ws)
+                ref_rows = x[:mb].reshape(mb * S, h).float()
+                self.errs.append(((rows.float() - ref_rows).abs().max() / ref_rows.abs().max()).item())
             self.x, self.n = x, self.n + 1
 
     res = {"oracle": "oracle/opt_ref.py (reference op sequence, torch eager on the same GPU, full depth, unsharded)", "weights": mode}
@@ -304,11 +322,16 @@ def parity_check(m, cfg, args, st, ids_dev, out_tokens, rank, world, dev):
         Hh = cfg.num_attention_heads
         cache = [(torch.zeros(S + n_steps, B, Hh, h // Hh, dtype=torch.bfloat16, device=dev),
                   torch.zeros(S + n_steps, B, Hh, h // Hh, dtype=torch.bfloat16, device=dev)) for _ in range(L)]   # A:471-472
-        last = Last()
+        last = Last(opt_ref.embed(om, ids_dev, mask, 0) if per_layer else None)
         hid = opt_ref.decoder_forward(om, ids_dev, mask, cache, 0, collect=last)
+        if per_layer:
+            res["per_layer_rel_err_max"] = max(last.errs)
+            res["per_layer_rel_err_mean"] = sum(last.errs) / len(last.errs)
+            res["per_layer_note"] = (f"each of the {L} layers run by this build on the ORACLE's input of that layer (first minibatch, {mb} x {S} rows): "
+                                     "the north-star bound is 1e-2 per layer")
         ours = st.x.view(B, S, h).float()
         ref = last.x.float()
-        res["prefill_hidden_rel_err"] = ((ours - ref).abs().max() / ref.abs().max()).item()
+        res["prefill_hidden_rel_err"] = ((ours - ref).abs().max() / ref.abs().max()).item()   # CHAINED over all layers
         res["prefill_hidden_rows"] = B * S
         del ours, ref, last
         # greedy tokens: free-running oracle vs the tokens the timed generate() returned
@@ -378,6 +401,8 @@ def _main(args, json_out):
                    f" ({CONFIG_LABEL[args.config_name]})" if args.config_name else ""))
     config = {"workload": workload, "parallelism": f"tp{world}", "l2": "inputs_exceed_l2 (weights+KV per step >> 126 MB)",
               "cuda_graphs": not args.no_graphs}
+    if args.quick:
+        config["quick"] = "ONE warm-up pass, one timed pass with host buffers (value == e2e): a minutes-long PCIe-bound generate()"
 
     if args.impl == "reference":
         if rank != 0:
@@ -414,7 +439,8 @@ def _main(args, json_out):
     c0 = _lib.launch_count
     m.generate(ids_dev, **kw)
     launches_per_step = _lib.launch_count - c0
-    for _ in range(max(args.warmup, 3) - 1):
+    n_warm = 1 if args.quick else max(args.warmup, 3)
+    for _ in range(n_warm - 1):
         m.generate(ids_dev, **kw)
     dec = m.model.decoder
     stream0 = dec.streamer.stats() if dec.streamer is not None else None
@@ -436,9 +462,12 @@ def _main(args, json_out):
         return sec, out, prefill, decode
 
     with ClockSampler(local) as clk:
-        sec, out, prefill, decode = timed(ids_dev)
+        sec, out, prefill, decode = timed(ids_host if args.quick else ids_dev)
     stream1 = dec.streamer.stats() if dec.streamer is not None else None
-    sec_e2e, out_h, _, _ = timed(ids_host)
+    if args.quick:      # one timed pass only, through the public call with host buffers: `value` and `e2e` are the same measurement
+        sec_e2e, out_h = sec, out.cpu()
+    else:
+        sec_e2e, out_h, _, _ = timed(ids_host)
     assert out_h.device.type == "cpu" and out_h.shape == (B, S + new)
     tok = B * new * args.steps
     value, e2e = tok / sec, tok / sec_e2e
@@ -523,7 +552,7 @@ def _main(args, json_out):
 
     if rank == 0:
         line = {"metric": "tokens/s", "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
+                "warmup": n_warm, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
                 "clocks": clk.summary(),
                 "e2e": {"value": e2e, "unit": "tokens/s", "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": B * (S + new) * 8},

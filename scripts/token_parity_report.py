@@ -41,7 +41,8 @@ def main(argv):
     L, B, S, new = (int(a) for a in (argv[1:5] + ["3", "8", "256", "32"][len(argv[1:5]):]))
     dev = "cuda" if torch.cuda.is_available() else "cpu"
     cfg = lia_b200.modeling_opt.get_config(name)
-    cfg.num_hidden_layers = L
+    if L > 0:
+        cfg.num_hidden_layers = L
     m = lia_b200.OPTForCausalLM(cfg, dev).init_weights(seed=3, bias_std=0.02, ln_std=0.05)
     om = oracle_model(m, dev)
     ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(1234)).to(dev)
@@ -68,7 +69,7 @@ def main(argv):
             mask = torch.cat([mask, mask.new_ones(B, 1)], dim=-1)
             logits, past = m(input_ids=want[:, None].contiguous(), attention_mask=mask, past_key_values=past, max_new_tokens=new)
     worst = max((f["ulps"] for f in flips), default=0.0)
-    print(json.dumps({"model": name, "layers": L, "B": B, "S": S, "new": new, "decisions": B * new, "identical": agree,
+    print(json.dumps({"model": name, "layers": cfg.num_hidden_layers, "B": B, "S": S, "new": new, "decisions": B * new, "identical": agree,
                       "flips": len(flips), "worst_flip_margin_ulps": worst, "flip_list": flips[:40]}))
 
 
