@@ -327,6 +327,7 @@ def parity_check(m, cfg, args, st, ids_dev, out_tokens, rank, world, dev):
         if per_layer:
             res["per_layer_rel_err_max"] = max(last.errs)
             res["per_layer_rel_err_mean"] = sum(last.errs) / len(last.errs)
+            res["per_layer_rel_err_over_1e-2"] = sum(1 for e in last.errs if e > 1e-2)
             res["per_layer_note"] = (f"each of the {L} layers run by this build on the ORACLE's input of that layer (first minibatch, {mb} x {S} rows): "
                                      "the north-star bound is 1e-2 per layer")
         ours = st.x.view(B, S, h).float()
