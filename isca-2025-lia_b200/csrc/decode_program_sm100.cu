@@ -79,11 +79,6 @@ __device__ __forceinline__ void wait_arrivals(const int* sync, int target, int* 
   }
 }
 
-// ring slots (k-blocks) this CTA's span of a GEMM covers
-__device__ __forceinline__ unsigned gemm_slots(const DecodeOp& op, int cta) {
-  Sched<true> s(op.k_blocks, op.tiles_a, 1, op.streamk, false, cta, op.ncta);
-  return s.end - s.pos;
-}
 // (b,h) pairs of an attention operation this CTA owns, and K (= V) tiles per pair
 __device__ __forceinline__ int attn_pairs(const DecodeOp& op, int cta, int ncta) {
   const int total = op.B * op.H;
@@ -558,7 +553,6 @@ int make_tmap_plain(CUtensorMap* map, const void* base, uint64_t rows, uint64_t 
 }
 
 int bn_for_rows(int M) { return M <= 16 ? 16 : M <= 32 ? 32 : M <= 64 ? 64 : 128; }
-int stages_for_bn(int bn) { return bn == 128 ? 4 : 8; }
 int stage_bytes_for_bn(int bn) { return TILE_A * BLOCK_K * 2 + bn * BLOCK_K * 2; }
 
 }  // namespace

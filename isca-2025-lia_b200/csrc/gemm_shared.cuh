@@ -658,11 +658,6 @@ bool pair_enabled() {
   return env == nullptr || atoi(env) != 0;
 }
 
-bool bn224_enabled() {
-  const char* env = getenv("LIA_GEMM_BN224");
-  return env != nullptr && atoi(env) != 0;
-}
-
 Plan make_plan(int M, int N, int K, bool allow_pair = false) {
   Plan pl;
   pl.pair = false;
@@ -688,14 +683,6 @@ Plan make_plan(int M, int N, int K, bool allow_pair = false) {
     pl.bn = (N % 256 == 0 || N >= 2048) ? 256 : 128;
     pl.pair = allow_pair && pl.bn == 256 && M >= 4 * TILE_A && sms >= 2 && pair_enabled();
     pl.tiles_a = pl.pair ? (M + 2 * TILE_A - 1) / (2 * TILE_A) : (M + TILE_A - 1) / TILE_A;
-    if (pl.pair && N % 224 == 0 && bn224_enabled()) {
-      // opt-in (LIA_GEMM_BN224=1, until A/B-checked on hardware): 256 x 224 tiles where they shorten the schedule.
-      // N = 7168, M = 8192 on 74 CTA pairs: 896 tiles of 256 = 12.1 waves -> 13 x 256 columns of work per pair;
-      // 1024 tiles of 224 = 13.8 waves -> 14 x 224 = 5.8 % less.  Same K order per element: bit-identical results.
-      const long long pairs = sms / 2;
-      const long long u256 = (long long)pl.tiles_a * ((N + 255) / 256), u224 = (long long)pl.tiles_a * (N / 224);
-      if (((u224 + pairs - 1) / pairs) * 224 < ((u256 + pairs - 1) / pairs) * 256) pl.bn = 224;
-    }
     pl.tiles_b = (N + pl.bn - 1) / pl.bn;
     const int units = pl.tiles_a * pl.tiles_b;
     if (pl.pair) pl.grid = 2 * (units < sms / 2 ? units : sms / 2);

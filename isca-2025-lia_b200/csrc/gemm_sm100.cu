@@ -42,11 +42,9 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                         const __grid_constant__ EpiParams p,
                         int k_blocks, int streamk, int tiles_a, int tiles_b, float* __restrict__ ws,
                         int* __restrict__ flags, unsigned long long* __restrict__ trace) {
-  static_assert(!PAIR || (!SWAP && !TP && (BN == 256 || BN == 224)), "CTA pairs: plain prefill projections with 256/224-wide tiles only");
+  static_assert(!PAIR || (!SWAP && !TP && BN == 256), "CTA pairs: plain prefill projections with 256-wide tiles only");
   using L = SmemLayout<SWAP, BN, STAGES, PAIR>;
-  // TMEM columns from one accumulator to the other: BN, rounded up to the epilogue's 64-column step for tile widths that
-  // are not a multiple of it (BN = 224, the opt-in tile that trims the wave tail of the N = 7168 projections)
-  constexpr int ACC_COLS = (SWAP || BN % 64 == 0) ? BN : ((BN + 63) / 64) * 64;
+  constexpr int ACC_COLS = BN;   // TMEM columns from one accumulator to the other
   // PAIR: rank in the 2-CTA cluster; rank 0 (the "leader") issues every MMA and owns the full / tempty barriers
   const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;
   extern __shared__ uint8_t smem_raw[];
@@ -633,7 +631,7 @@ static int gemm_impl(const void* A, const void* W, const void* bias, const void*
   } else {
     if ((rc = make_tmap(&tmA, A, M, K, TILE_A)) != LIA_OK) return rc;
     if ((rc = make_tmap(&tmB, W, N, K, pl.pair ? pl.bn / 2 : pl.bn)) != LIA_OK) return rc;
-    if (pl.pair) return pl.bn == 224 ? launch_pair<224>(pl, tmA, tmB, ep, stream) : launch_pair<256>(pl, tmA, tmB, ep, stream);
+    if (pl.pair) return launch_pair<256>(pl, tmA, tmB, ep, stream);
     if (pl.bn == 256) return launch<false, 256, 4>(pl, tmA, tmB, ep, ws, flags, stream);
     return launch<false, 128, 6>(pl, tmA, tmB, ep, ws, flags, stream);
   }

@@ -30,10 +30,8 @@ for label, N, K, epi in [("qkv", 3 * h, h, 0), ("out", h, h, 2), ("fc1", f, h, 1
     res = torch.randn(M, N, device=dev).to(torch.bfloat16) if epi == 2 else None
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     outs = {}
-    for flag, bn224 in (("0", "0"), ("1", "0"), ("1", "1")):
-        # LIA_GEMM_BN224=1 (opt-in): 256 x 224 pair tiles where they shorten the schedule (N = 7168: 13.8 waves of 224
-        # instead of 12.1 -> 13 waves of 256); same K order per element, so the output must be bit-identical
-        os.environ["LIA_GEMM_2CTA"], os.environ["LIA_GEMM_BN224"] = flag, bn224
+    for flag, bn224 in (("0", "0"), ("1", "0")):
+        os.environ["LIA_GEMM_2CTA"] = flag
         ms = timeit(lambda i: ops.gemm(a, ws_[i % 2], bias, out=out, epilogue=epi, residual=res))
         outs[(flag, bn224)] = ops.gemm(a, ws_[0], bias, epilogue=epi, residual=res)
         torch.cuda.synchronize()

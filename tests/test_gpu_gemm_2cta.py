@@ -66,26 +66,3 @@ def test_pair_gemm_qkv_scatter_and_model(ops, monkeypatch):
     assert torch.equal(outs[0], outs[1])
     for k0, k1 in zip(*caches):
         assert torch.equal(k0, k1)
-
-
-@pytest.mark.skipif(__import__("os").environ.get("LIA_TEST_OPTIN", "0") == "0",
-                    reason="opt-in kernel variant (not yet a default): run with LIA_TEST_OPTIN=1, as scripts/gpu_round2.sh does")
-@pytest.mark.parametrize("M,N,K", [(512, 224, 64), (1024, 448, 512), (8192, 7168, 7168), (777, 2240, 520), (2048, 7168, 28672),
-                                   (8192, 21504, 7168)])
-@pytest.mark.parametrize("epilogue", [0, 1, 2])
-def test_pair_gemm_bn224_matches_bn256(ops, monkeypatch, M, N, K, epilogue):
-    """LIA_GEMM_BN224=1: 256 x 224 CTA-pair tiles (chosen only where they shorten the schedule) accumulate every element
-    over K in the same order as the 256 x 256 tiles, so the outputs must agree bit for bit."""
-    a = rnd(M, K, seed=M + N)
-    w = rnd(N, K, std=K ** -0.5, seed=K + 1)
-    bias = rnd(N, std=0.5, seed=5)
-    res = rnd(M, N, seed=6) if epilogue == 2 else None
-    monkeypatch.setenv("LIA_GEMM_2CTA", "1")
-    monkeypatch.setenv("LIA_GEMM_BN224", "0")
-    y1 = ops.gemm(a, w, bias, epilogue=epilogue, residual=res)
-    monkeypatch.setenv("LIA_GEMM_BN224", "1")
-    for rep in range(2):
-        y2 = ops.gemm(a, w, bias, epilogue=epilogue, residual=res)
-        torch.cuda.synchronize()
-        ndiff = int((y1.view(torch.int16) != y2.view(torch.int16)).sum())
-        assert ndiff == 0, f"{M}x{N}x{K} epi {epilogue} rep {rep}: {ndiff} of {y1.numel()} elements differ from the 256-wide tiles"
