@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libliab200.so")
 
 EPI_BIAS, EPI_BIAS_RELU, EPI_BIAS_RESIDUAL, EPI_QKV = 0, 1, 2, 3
-ABI_VERSION = 4
+ABI_VERSION = 5
 TP_MAX_WORLD = 8
 P2P_HANDLE_BYTES = 64
 
@@ -26,7 +26,7 @@ class LiaQkvArgs(ctypes.Structure):
 class LiaTpArgs(ctypes.Structure):
     _fields_ = [("rank", c_int32), ("world", c_int32), ("arena", c_void_p * TP_MAX_WORLD),
                 ("ctl_off", ctypes.c_uint64), ("recv_off", ctypes.c_uint64), ("recv_bytes", ctypes.c_uint64),
-                ("out_off", ctypes.c_uint64)]
+                ("out_off", ctypes.c_uint64), ("mc_arena", c_void_p)]
 
 
 class LiaError(RuntimeError):

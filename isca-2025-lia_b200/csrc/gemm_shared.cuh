@@ -26,6 +26,7 @@ struct TpDev {
   int rank, world;
   int opts;   // tuning probes: bit0 = do not trigger dependents early (PDL), bit1 = back off between failed polls
   char* arena[LIA_TP_MAX_WORLD];
+  char* mc;   // multicast mapping of the arena (NVLS) or nullptr
   unsigned long long ctl_off, recv_off, recv_bytes, out_off;
   __device__ __forceinline__ int* ctl(int r) const { return reinterpret_cast<int*>(arena[r] + ctl_off); }
   // data_flag[unit][src]: rank `src`'s partial of `unit` has landed in rank r's receive area
@@ -215,6 +216,21 @@ __device__ __forceinline__ uint4 ld_volatile_v4(const uint4* p) {
   asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
+// NVLink-switch multicast (NVLS): ONE address stands for the same location of every rank's arena.
+//   multimem.ld_reduce  returns the SUM over all ranks' copies (8 bf16 per call, fp32 accumulation inside the switch)
+//   multimem.st         stores to every rank's copy
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // wait until *flag reaches `epoch` (flags only grow; wrap-safe compare).  A peer that never shows up
 // must not hang the GPU: after TP_TIMEOUT_NS the error word is set and every later wait falls through.
 __device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
@@ -764,6 +780,11 @@ inline int gemm_fill_params(const void* A, const void* W, const void* bias, cons
     ep.tp.world = tp->world;
     for (int r = 0; r < tp->world; ++r) ep.tp.arena[r] = reinterpret_cast<char*>(tp->arena[r]);
     ep.tp.ctl_off = tp->ctl_off; ep.tp.recv_off = tp->recv_off; ep.tp.recv_bytes = tp->recv_bytes; ep.tp.out_off = tp->out_off;
+    ep.tp.mc = reinterpret_cast<char*>(tp->mc_arena);
+    {
+      const char* e = getenv("LIA_TP_NVLS");         // 0: ignore the multicast mapping (A/B against the peer-store exchange)
+      if (e && atoi(e) == 0) ep.tp.mc = nullptr;
+    }
   }
   return LIA_OK;
 }

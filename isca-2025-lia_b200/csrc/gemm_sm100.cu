@@ -243,6 +243,42 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       constexpr int CPR = BN / 8;             // 16-byte chunks per tile row
       constexpr int CH = 8;                   // chunks per thread in flight: (1 + world) x 8 independent 16-byte loads
       static_assert(SWAP || !TP || (TILE_A * CPR) % (128 * CH) == 0, "tile must split into whole batches");
+      if (tp.mc != nullptr) {
+        // NVLS: every rank's partial of tile u sits at the same offset of its OWN arena; one multimem.ld_reduce returns the
+        // sum of the `world` copies (reduced inside the NVLink switch, fp32 accumulation, one bf16 rounding = the
+        // reference's message dtype), one multimem.st delivers the final chunk to every rank's `out`
+        const char* mpart = tp.mc + tp.recv_off + (unsigned long long)parity * tp.recv_bytes + (size_t)u * (TILE_A * BN) * 2;
+#pragma unroll 1
+        for (int c0 = et; c0 < TILE_A * CPR; c0 += 128 * CH) {
+          uint4 sumv[CH], res[CH];
+          bool ok[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            const int c = c0 + j * 128;
+            const int row = c / CPR, ch = c - row * CPR;
+            const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
+            ok[j] = (m < p.M && n < p.N);
+            res[j] = ok[j] ? ldg_act(p.residual + (size_t)m * p.N + n) : make_uint4(0, 0, 0, 0);
+            sumv[j] = ok[j] ? multimem_ld_reduce_bf16x8(mpart + ((size_t)row * BN + ch * 8) * 2) : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int j = 0; j < CH; ++j) {
+            if (ok[j]) {
+              const int c = c0 + j * 128;
+              const int row = c / CPR, ch = c - row * CPR;
+              const int m = ta * TILE_A + row, n = tb * BN + ch * 8;
+              float f[8], r[8];
+              unpack8(sumv[j], f);
+              unpack8(res[j], r);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) f[i] = r[i] + f[i];
+              multimem_st_bf16x8(tp.mc + tp.out_off + ((size_t)m * p.N + n) * 2, pack8(f));
+            }
+          }
+        }
+        sig_done_u = u;
+        return;
+      }
 #pragma unroll 1
       for (int c0 = et; c0 < TILE_A * CPR; c0 += 128 * CH) {
         float sum[CH][8];
@@ -400,7 +436,10 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
                   for (int i = 0; i < 8; ++i) f[i] = bf16r(f[i] + bias_s[i]);
                 }
                 const int u = w.ta * tiles_b + w.tb;
-                bf16* dst = tp.recv(u % tp.world, parity) + ((size_t)(u / tp.world) * tp.world + tp.rank) * (TILE_A * BN) +
+                // peer-store exchange: straight into the owner's receive area, slot [tile][this rank];
+                // NVLS exchange: into OUR OWN arena at the tile's offset (the switch reads it from there)
+                bf16* dst = (tp.mc != nullptr ? tp.recv(tp.rank, parity) + (size_t)u * (TILE_A * BN)
+                                              : tp.recv(u % tp.world, parity) + ((size_t)(u / tp.world) * tp.world + tp.rank) * (TILE_A * BN)) +
                             (size_t)(ew * 32 + r) * BN + c0 + ch * 8;
                 *reinterpret_cast<uint4*>(dst) = pack8(f);
               } else {
@@ -416,6 +455,7 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (owner != tp.rank) {
             sig_data_u = u;
           } else {
+            if (tp.mc != nullptr) __threadfence_system();   // NVLS: the switch reads our own partial from memory too
             epi_bar_sync();                      // our own partial is complete in our receive area
             // defer the reduction by one owned tile (= `world` tiles of MMA work) so the peers' partials are
             // normally already here and the epilogue warps never stall the tensor pipe on NVLink latency

@@ -154,9 +154,12 @@ class _GenState:
             lay, lib = model.layout, _lib.load()
             recv = max(lib.lia_tp_recv_bytes(m, h, k, model.tp_world) for m in {mb * S, B} for k in (lay.hq, lay.fq))
             loop = os.environ.get("LIA_TP_SELF_LOOP", "0") != "0"      # timing probe: one process, peers = itself
-            self.arena = tp_mod.PeerArena(model.tp_rank, model.tp_world, dev, recv,
-                                          [("x", B * S * h * 2), ("xd", B * h * 2), ("x1", rows * h * 2)],
-                                          exchange=(lambda mine: [0] * model.tp_world) if loop else None)
+            # symmetric memory with an NVLink-switch multicast mapping where the pod has one (in-switch reduction of the
+            # prefill exchange), CUDA-IPC peer mappings otherwise
+            arena_cls = tp_mod.SymmArena if (not loop and tp_mod.SymmArena.available(dev)) else tp_mod.PeerArena
+            self.arena = arena_cls(model.tp_rank, model.tp_world, dev, recv,
+                                   [("x", B * S * h * 2), ("xd", B * h * 2), ("x1", rows * h * 2)],
+                                   exchange=(lambda mine: [0] * model.tp_world) if loop else None)
             if loop:
                 self.arena.peers = [self.arena.local] * model.tp_world
             self.x = self.arena.tensor("x", (B * S, h))

@@ -104,6 +104,14 @@ class PeerArena:
             self.offsets[name] = (off, int(nbytes))
             off = _align(off + nbytes)
         self.nbytes = off
+        self.mc = None                           # multicast mapping of the arena (SymmArena)
+        self._alloc(group, exchange)
+        self._bytes = torch.as_tensor(_RawCuda(self.local, self.nbytes), device=self.device)
+
+    def _alloc(self, group, exchange):
+        """cudaMalloc + CUDA IPC (lia_p2p_*): every peer maps this rank's arena; handles travel through torch.distributed."""
+        lib = _lib.load()
+        rank, world = self.rank, self.world
         ptr = ctypes.c_void_p()
         handle = (ctypes.c_uint8 * _lib.P2P_HANDLE_BYTES)()
         with torch.cuda.device(self.device):
@@ -130,7 +138,6 @@ class PeerArena:
                 _lib.check(lib.lia_p2p_open(h, ctypes.byref(pp)), "lia_p2p_open")
             self.peers[r] = pp.value
             self._opened.append(pp.value)
-        self._bytes = torch.as_tensor(_RawCuda(self.local, self.nbytes), device=self.device)
 
     def tensor(self, name, shape, dtype=torch.bfloat16):
         off, nbytes = self.offsets[name]
@@ -154,6 +161,7 @@ class PeerArena:
             a.arena[r] = self.peers[r]
         a.ctl_off, a.recv_off, a.recv_bytes = self.ctl_off, self.recv_off, self.recv_bytes
         a.out_off = self.offset_of(out) if out is not None else 0
+        a.mc_arena = self.mc
         return a
 
     def check(self):
@@ -181,3 +189,57 @@ class PeerArena:
         # cudaFree / cudaDeviceSynchronize inside an open graph capture would invalidate it: park the free (graphs.py)
         if getattr(self, "local", None):
             graphs.finalize(lambda: self.close(sync=False))
+
+
+
+class SymmArena(PeerArena):
+    """The same arena on SYMMETRIC memory bound to an NVLink-switch multicast object: besides every peer's mapping there is
+    ONE multicast address behind which all ranks' copies sit, so the prefill exchange can reduce inside the switch
+    (``multimem.ld_reduce``) and deliver with one store (``multimem.st``).  Allocation and rendezvous are
+    ``torch.distributed._symmetric_memory`` (CUDA VMM + fabric handles + cuMulticast*): plumbing, like the IPC exchange of
+    ``PeerArena``; the data path is the kernel's own multimem instructions.  ``available()`` says whether this process group
+    can have one (NVSwitch + a driver that exposes multicast); otherwise ``PeerArena`` is used."""
+
+    _probe = None
+
+    @staticmethod
+    def available(device):
+        if os.environ.get("LIA_TP_SYMM", "1") == "0" or not dist.is_initialized() or dist.get_backend() != "nccl":
+            return False
+        if SymmArena._probe is None:
+            ok = False
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                t = symm_mem.empty(4096, dtype=torch.uint8, device=torch.device(device))
+                h = symm_mem.rendezvous(t, dist.group.WORLD.group_name)
+                ok = int(h.multicast_ptr) != 0
+                SymmArena._keep_probe = (t, h)
+            except Exception:
+                ok = False
+            flag = torch.tensor([1 if ok else 0], device=torch.device(device))
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)          # every rank must agree
+            SymmArena._probe = bool(flag.item())
+        return SymmArena._probe
+
+    def _alloc(self, group, exchange):
+        import torch.distributed._symmetric_memory as symm_mem
+        self._symm = symm_mem.empty(self.nbytes, dtype=torch.uint8, device=self.device)
+        self._symm.zero_()
+        torch.cuda.synchronize(self.device)
+        self._hdl = symm_mem.rendezvous(self._symm, dist.group.WORLD.group_name)
+        self.local = self._symm.data_ptr()
+        self.peers = [int(p) for p in self._hdl.buffer_ptrs]
+        self.peers[self.rank] = self.local
+        self.mc = int(self._hdl.multicast_ptr) or None
+        self._opened = []
+        dist.barrier()                            # every rank's arena is zeroed before anyone's kernel touches it
+
+    def close(self, sync=True):
+        if getattr(self, "local", None):
+            torch.cuda.synchronize(self.device)
+            if sync and dist.is_initialized():
+                dist.barrier()
+            self._bytes = None
+            self.local = None
+            self._hdl = None
+            self._symm = None

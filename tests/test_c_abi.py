@@ -37,12 +37,12 @@ def test_header_symbols_exported_and_bound(built):
 
 def test_abi_version_and_struct_layout(built):
     lib = built.load()
-    assert lib.lia_abi_version() == built.ABI_VERSION == 4
+    assert lib.lia_abi_version() == built.ABI_VERSION == 5
     # LiaQkvArgs: 3 pointers + 5 int32 + 1 float, natural alignment
     assert ctypes.sizeof(built.LiaQkvArgs) == 48
     assert built.LiaQkvArgs.hq.offset == 24 and built.LiaQkvArgs.q_scale.offset == 44
     # LiaTpArgs: 2 int32 + 8 pointers + 4 uint64
-    assert ctypes.sizeof(built.LiaTpArgs) == 8 + 64 + 32 and built.LiaTpArgs.ctl_off.offset == 72
+    assert ctypes.sizeof(built.LiaTpArgs) == 8 + 64 + 32 + 8 and built.LiaTpArgs.ctl_off.offset == 72 and built.LiaTpArgs.mc_arena.offset == 104
     assert lib.lia_tp_ctl_bytes() == (64 + 16384 * 8 + 16384) * 4
     # receive area for M <= 128: [world][bn][N] partials + [bn][N] two-shot finals as {bf16x2, epoch} words;
     # above: two-shot [owned tiles][world][128][bn]

@@ -27,15 +27,21 @@ def main():
     torch.cuda.set_device(dev)
     lib = _lib.load()
 
-    # ---- 1. kernel level
-    for (M, N, K) in [(8, 256, 512), (64, 7168, 896), (64, 1024, 3584), (384, 512, 256), (4096, 7168, 896), (1000, 768, 320)]:
+    # ---- 1. kernel level: the CUDA-IPC arena (peer-store exchange) and, where the pod has NVLink-switch multicast, the
+    # symmetric-memory arena (prefill shapes then reduce inside the switch: multimem.ld_reduce / multimem.st)
+    kinds = [tp.PeerArena] + ([tp.SymmArena] if tp.SymmArena.available(dev) else [])
+    if rank == 0:
+        print("arena kinds:", [k.__name__ for k in kinds], flush=True)
+    for arena_cls, (M, N, K) in [(a, s_) for a in kinds for s_ in [(8, 256, 512), (64, 7168, 896), (64, 1024, 3584), (384, 512, 256),
+                                                                  (4096, 7168, 896), (1000, 768, 320)]]:
         g = torch.Generator(device="cuda").manual_seed(1000 * rank + M)
         a = (torch.randn(M, K, generator=g, device=dev) * 0.5).to(BF16)
         w = (torch.randn(N, K, generator=g, device=dev) * 0.5).to(BF16)
         b = (torch.randn(N, generator=g, device=dev) * 0.5).to(BF16)
         g2 = torch.Generator(device="cuda").manual_seed(7)
         res = (torch.randn(M, N, generator=g2, device=dev)).to(BF16)           # replicated residual stream
-        arena = tp.PeerArena(rank, world, dev, lib.lia_tp_recv_bytes(M, N, K, world), [("out", M * N * 2)])
+        arena = arena_cls(rank, world, dev, lib.lia_tp_recv_bytes(M, N, K, world), [("out", M * N * 2)])
+        nvls = arena.mc is not None and M > 128          # in-switch sum: fp32 like ours, but in the switch's order
         out = arena.tensor("out", (M, N))
         ws = ops.GemmWorkspace(ops.GemmWorkspace.bytes_for([(M, N, K)]), dev)
         part = ops.gemm(a, w, b, epilogue=ops.EPI_BIAS, workspace=ws)
@@ -50,7 +56,7 @@ def main():
             ops.gemm_allreduce(a, w, b, res, out, args, workspace=ws)
             torch.cuda.synchronize()
             arena.check()
-            assert torch.equal(out, want), (rank, M, N, K, rep, (out.float() - want.float()).abs().max().item())
+            _same(out, want, nvls and world > 2, (rank, arena_cls.__name__, M, N, K, rep))
         gr = torch.cuda.CUDAGraph()
         with graphs.capture(gr):
             ops.gemm_allreduce(a, w, b, res, out, args, workspace=ws)
@@ -60,14 +66,15 @@ def main():
             gr.replay()
             torch.cuda.synchronize()
             arena.check()
-            assert torch.equal(out, want), (rank, "graph", M, N, K, rep)
+            _same(out, want, nvls and world > 2, (rank, arena_cls.__name__, "graph", M, N, K, rep))
         alls = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(alls, out.contiguous())
         assert all(torch.equal(alls[0], x) for x in alls)
         del gr
         arena.close()
         if rank == 0:
-            print(f"fused gemm+allreduce M={M} N={N} K={K} world={world}: exact", flush=True)
+            print(f"fused gemm+allreduce [{arena_cls.__name__}{' NVLS' if nvls else ''}] M={M} N={N} K={K} world={world}: "
+                  f"{'within 1 ulp of the rank-order sum, identical on every rank' if nvls and world > 2 else 'exact'}", flush=True)
 
     # ---- 2. model level
     cfg = lia_b200.OPTConfig(hidden_size=512, num_hidden_layers=4, num_attention_heads=8, ffn_dim=2048, vocab_size=1024,
@@ -86,6 +93,17 @@ def main():
     os._exit(0)
 
 
+def _same(out, want, loose, what):
+    """Exact, except that a sum formed inside the NVLink switch over more than two ranks may round differently from the
+    rank-order fp32 sum: then within one bf16 ulp of the summed message (the residual add follows the rounding)."""
+    if not loose:
+        assert torch.equal(out, want), (what, (out.float() - want.float()).abs().max().item())
+        return
+    d = (out.float() - want.float()).abs()
+    tol = 2.0 ** (torch.floor(torch.log2(want.float().abs().clamp_min(1e-3))) - 7) * 2
+    assert bool((d <= tol).all()), (what, d.max().item())
+
+
 def _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb):
     ids = torch.randint(3, cfg.vocab_size, (B, S), generator=torch.Generator().manual_seed(3))
     one = lia_b200.OPTForCausalLM(cfg, dev).init_weights(seed=5, bias_std=0.02, ln_std=0.05)
@@ -97,8 +115,8 @@ def _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb):
     tok_ref = one.generate(ids, max_new_tokens=new, min_new_tokens=new, num_minibatch=nmb)
     top2 = logits_ref.topk(2, dim=-1).values
     safe = (top2[:, 0] - top2[:, 1]) > 8 * 2 ** -8 * top2[:, 0].abs().clamp_min(1.0)
-    for fused in ("1", "0"):
-        os.environ["LIA_TP_FUSED"] = fused
+    for fused, symm in (("1", "1"), ("1", "0"), ("0", "1")):
+        os.environ["LIA_TP_FUSED"], os.environ["LIA_TP_SYMM"] = fused, symm
         m = lia_b200.OPTForCausalLM(cfg, dev, tp_rank=rank, tp_world=world).init_weights(seed=5, bias_std=0.02, ln_std=0.05)
         st = m._state(B, S, new, nmb)
         assert (st.arena is not None) == (fused == "1")
@@ -116,7 +134,7 @@ def _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb):
         assert all(torch.equal(alls[0], x) for x in alls), "ranks disagree on greedy tokens"
         if rank == 0:
             agree = (toks[0].cpu() == tok_ref.cpu()).float().mean().item()
-            print(f"TP{world} fused={fused} B={B} S={S} nmb={nmb}: prefill hidden rel err {err:.2e}; token agreement with TP1 {agree:.3f}; "
+            print(f"TP{world} fused={fused} arena={type(st.arena).__name__ if st.arena is not None else None} B={B} S={S} nmb={nmb}: prefill hidden rel err {err:.2e}; token agreement with TP1 {agree:.3f}; "
                   f"decode {1e3 * sum(m.last_timing['decode_s']) / (new - 1):.3f} ms/step", flush=True)
         for s_ in m._states.values():
             if s_.arena is not None:
