@@ -782,8 +782,11 @@ inline int gemm_fill_params(const void* A, const void* W, const void* bias, cons
     ep.tp.ctl_off = tp->ctl_off; ep.tp.recv_off = tp->recv_off; ep.tp.recv_bytes = tp->recv_bytes; ep.tp.out_off = tp->out_off;
     ep.tp.mc = reinterpret_cast<char*>(tp->mc_arena);
     {
-      const char* e = getenv("LIA_TP_NVLS");         // 0: ignore the multicast mapping (A/B against the peer-store exchange)
-      if (e && atoi(e) == 0) ep.tp.mc = nullptr;
+      // In-switch reduction moves S (every partial, once) + S/world bytes per rank against 2 S (world-1)/world for the
+      // peer-store exchange: fewer from 4 ranks up (1.25 S vs 1.5 S; 1.125 S vs 1.75 S at 8), more at 2 (1.5 S vs S).
+      // LIA_TP_NVLS=0 / 1 forces it off / on (A/B runs, and the 2-GPU test of the multimem path).
+      const char* e = getenv("LIA_TP_NVLS");
+      if (e ? atoi(e) == 0 : tp->world < 4) ep.tp.mc = nullptr;
     }
   }
   return LIA_OK;

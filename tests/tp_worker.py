@@ -29,6 +29,7 @@ def main():
 
     # ---- 1. kernel level: the CUDA-IPC arena (peer-store exchange) and, where the pod has NVLink-switch multicast, the
     # symmetric-memory arena (prefill shapes then reduce inside the switch: multimem.ld_reduce / multimem.st)
+    os.environ["LIA_TP_NVLS"] = "1"              # also at 2 ranks, where the library would not choose it by itself
     kinds = [tp.PeerArena] + ([tp.SymmArena] if tp.SymmArena.available(dev) else [])
     if rank == 0:
         print("arena kinds:", [k.__name__ for k in kinds], flush=True)
@@ -56,7 +57,7 @@ def main():
             ops.gemm_allreduce(a, w, b, res, out, args, workspace=ws)
             torch.cuda.synchronize()
             arena.check()
-            _same(out, want, nvls and world > 2, (rank, arena_cls.__name__, M, N, K, rep))
+            _same(out, want, nvls, (rank, arena_cls.__name__, M, N, K, rep), tot)
         gr = torch.cuda.CUDAGraph()
         with graphs.capture(gr):
             ops.gemm_allreduce(a, w, b, res, out, args, workspace=ws)
@@ -66,7 +67,7 @@ def main():
             gr.replay()
             torch.cuda.synchronize()
             arena.check()
-            _same(out, want, nvls and world > 2, (rank, arena_cls.__name__, "graph", M, N, K, rep))
+            _same(out, want, nvls, (rank, arena_cls.__name__, "graph", M, N, K, rep), tot)
         alls = [torch.empty_like(out) for _ in range(world)]
         dist.all_gather(alls, out.contiguous())
         assert all(torch.equal(alls[0], x) for x in alls)
@@ -74,7 +75,7 @@ def main():
         arena.close()
         if rank == 0:
             print(f"fused gemm+allreduce [{arena_cls.__name__}{' NVLS' if nvls else ''}] M={M} N={N} K={K} world={world}: "
-                  f"{'within 1 ulp of the rank-order sum, identical on every rank' if nvls and world > 2 else 'exact'}", flush=True)
+                  f"{_same.last if nvls else 'exact'}", flush=True)
 
     # ---- 2. model level
     cfg = lia_b200.OPTConfig(hidden_size=512, num_hidden_layers=4, num_attention_heads=8, ffn_dim=2048, vocab_size=1024,
@@ -93,15 +94,24 @@ def main():
     os._exit(0)
 
 
-def _same(out, want, loose, what):
-    """Exact, except that a sum formed inside the NVLink switch over more than two ranks may round differently from the
-    rank-order fp32 sum: then within one bf16 ulp of the summed message (the residual add follows the rounding)."""
+def _same(out, want, loose, what, tot=None):
+    """Exact, except for sums formed inside the NVLink switch (multimem.ld_reduce: fp32 accumulation, then the switch's own
+    conversion to bf16): the summed message may differ from the rank-order sum by one bf16 ulp OF THE SUM (``tot``), which
+    the residual add then carries (plus its own rounding) into the result."""
     if not loose:
         assert torch.equal(out, want), (what, (out.float() - want.float()).abs().max().item())
         return
     d = (out.float() - want.float()).abs()
-    tol = 2.0 ** (torch.floor(torch.log2(want.float().abs().clamp_min(1e-3))) - 7) * 2
-    assert bool((d <= tol).all()), (what, d.max().item())
+    mag = torch.maximum(tot.abs(), want.float().abs()).clamp_min(1e-3)
+    tol = 2.0 ** (torch.floor(torch.log2(mag)) - 7) * 2
+    nz = d > 0
+    low = ((out.float().abs() < want.float().abs()) & nz).sum().item()
+    _same.last = (f"within 1 ulp of the rank-order sum ({nz.float().mean().item() * 100:.3f} % of the elements differ, "
+                  f"{low} of {int(nz.sum())} smaller in magnitude, worst {float((d / tol * 2).max()):.2f} ulp), identical on every rank")
+    assert bool((d <= tol).all()), (what, d.max().item(), _same.last)
+
+
+_same.last = ""
 
 
 def _model_case(lia_b200, tp, dist, cfg, dev, rank, world, B, S, new, nmb):
