@@ -227,10 +227,16 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     int sig_data_u = -1, sig_done_u = -1;
     auto tp_flush_signals = [&]() {
       if (sig_data_u >= 0 || sig_done_u >= 0) {
-        __threadfence_system();
+        // The CTA barrier orders every epilogue thread's stores of the covered tile before the signalling threads, whose
+        // st.release.sys is the release pattern that publishes them (release is cumulative over what the barrier made
+        // visible to the storing thread).  Round 1 had all 128 threads execute a system-scope fence here first: ~8 us per
+        // tile, 100 us per launch of a short-K projection where no MMA time hides it (scripts/tp_microbench.py, TP2
+        // out_proj prefill: 509 -> 405 us).
         epi_bar_sync();
-        if (sig_data_u >= 0 && et == 0) st_release_sys(tp.data_flag(sig_data_u % tp.world, sig_data_u, tp.rank), epoch);
-        if (sig_done_u >= 0 && et < tp.world && et != tp.rank) st_release_sys(tp.done_flag(et, sig_done_u), epoch);
+        if (et < tp.world) {
+          if (sig_data_u >= 0 && et == 0) st_release_sys(tp.data_flag(sig_data_u % tp.world, sig_data_u, tp.rank), epoch);
+          if (sig_done_u >= 0 && et != tp.rank) st_release_sys(tp.done_flag(et, sig_done_u), epoch);
+        }
         sig_data_u = sig_done_u = -1;
       }
     };
@@ -455,8 +461,8 @@ lia_gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (owner != tp.rank) {
             sig_data_u = u;
           } else {
-            if (tp.mc != nullptr) __threadfence_system();   // NVLS: the switch reads our own partial from memory too
             epi_bar_sync();                      // our own partial is complete in our receive area
+            if (tp.mc != nullptr && et == 0) __threadfence_system();   // NVLS: the switch reads our own partial from memory too
             // defer the reduction by one owned tile (= `world` tiles of MMA work) so the peers' partials are
             // normally already here and the epilogue warps never stall the tensor pipe on NVLink latency
             if (pend_u >= 0) tp_reduce_owned(pend_u, pend_ta, pend_tb);
