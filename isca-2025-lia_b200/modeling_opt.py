@@ -114,7 +114,8 @@ class _Workspace:
         h, hq, fq = cfg.hidden_size, layout.hq, layout.fq
         e = lambda *s: torch.empty(*s, dtype=BF16, device=device)  # noqa: E731
         self.rows = rows
-        self.arena = arena          # tp.PeerArena: row-parallel projections run fused with their all-reduce
+        self.arena = arena          # tp.PeerArena / SymmArena: row-parallel projections run fused with their all-reduce
+        self.arena_d = arena        # arena of the decode-shaped (M <= 128) exchanges, when it is a separate one
         self.ln, self.q, self.ctx, self.ffn = e(rows, h), e(rows, hq), e(rows, hq), e(rows, fq)
         self.x1 = arena.tensor("x1", (rows, h)) if arena is not None else e(rows, h)
         # decode (M <= 128) needs no remotely writable output: keep its residual stream out of the peer-mapped arena
@@ -147,7 +148,7 @@ class _GenState:
         mb = max(1, B // max(1, num_minibatch))
         rows = max(mb * S, B)
         h = cfg.hidden_size
-        self.arena = None
+        self.arena = self.arena_d = None
         if model.tp_world > 1 and tp_mod.fused_enabled() and dev.type == "cuda":
             # the residual stream lives in a peer-mapped arena: owners of a prefill tile write the reduced
             # result straight into every rank's copy (include/lia_b200.h, lia_gemm_allreduce_bf16)
@@ -162,6 +163,13 @@ class _GenState:
                                    exchange=(lambda mine: [0] * model.tp_world) if loop else None)
             if loop:
                 self.arena.peers = [self.arena.local] * model.tp_world
+            # decode-shaped exchanges (M <= 128: latency-bound LL stores into peers' receive areas) keep a CUDA-IPC arena of
+            # their own: measured 0.25 ms per decode step slower at TP4 through memory bound to a multicast object
+            # (profiles/README.md), while the prefill exchange gains from the in-switch reduction
+            self.arena_d = self.arena
+            if isinstance(self.arena, tp_mod.SymmArena) and S > 1 and os.environ.get("LIA_TP_DECODE_ARENA", "0") == "0":
+                recv_d = max(lib.lia_tp_recv_bytes(m, h, k, model.tp_world) for m in {min(mb * S, 128), B} for k in (lay.hq, lay.fq))
+                self.arena_d = tp_mod.PeerArena(model.tp_rank, model.tp_world, dev, recv_d, [("pad", 256)])
             self.x = self.arena.tensor("x", (B * S, h))
             self.xd = (self.arena.tensor("xd", (B, h)) if os.environ.get("LIA_TP_DECODE_ARENA", "0") != "0"
                        else torch.empty(B, h, dtype=BF16, device=dev))
@@ -171,6 +179,7 @@ class _GenState:
         self.xn = torch.empty(B, cfg.hidden_size, dtype=BF16, device=dev)
         self.logits = torch.empty(B, cfg.vocab_size, dtype=BF16, device=dev)
         self.ws = _Workspace(cfg, model.layout, rows, B, dev, self.arena)
+        self.ws.arena_d = getattr(self, "arena_d", None)
         self.graphs = {}
         self.program = None         # program.DecodeProgram: the whole decode step as one persistent kernel (False: unsupported)
         self.calls = 0
@@ -206,6 +215,9 @@ class _GenState:
             self.program.close()
         self.program = None
         self.graphs = {}
+        if getattr(self, "arena_d", None) is not None and self.arena_d is not self.arena:
+            self.arena_d.close()
+        self.arena_d = None
         if self.arena is not None:
             self.arena.close()
             self.arena = None
@@ -417,7 +429,8 @@ class OPTDecoder:
             self.k.gemm(a, w, b, out=out, epilogue=EPI_BIAS_RESIDUAL, residual=residual, workspace=ws.gemm)   # D:228-229, 309-310
         elif arena is not None:             # D:60-68 + 247/317 as one kernel over NVLink peer memory
             # prefill tiles are finished by their owner rank, which writes `out` remotely: it must live in the arena
-            self.k.gemm_allreduce(a, w, b, residual, out, arena.args(out if big else None), workspace=ws.gemm)
+            args = arena.args(out) if big else (ws.arena_d or arena).args(None)
+            self.k.gemm_allreduce(a, w, b, residual, out, args, workspace=ws.gemm)
         else:
             part = ws.tp[:a.shape[0]]
             self.k.gemm(a, w, b, out=part, epilogue=EPI_BIAS, workspace=ws.gemm)                              # D:60-68
@@ -749,6 +762,8 @@ class OPTForCausalLM:
         torch.cuda.synchronize(self.device)
         if st.arena is not None and os.environ.get("LIA_TP_SELF_LOOP", "0") == "0":
             st.arena.check()                          # a peer that never showed up: raise instead of returning garbage
+            if st.arena_d is not st.arena:
+                st.arena_d.check()
         if prog is not None:
             prog.check()                              # a CTA that timed out on a dependency: raise, do not return garbage
         lat = [ev[i].elapsed_time(ev[i + 1]) / 1e3 for i in range(new)]
