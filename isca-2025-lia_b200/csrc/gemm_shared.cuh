@@ -80,15 +80,18 @@ __device__ __forceinline__ void epilogue_finish8(const EpiParams& p, int m, int 
     for (int i = 0; i < 8; ++i) v[i] = r[i] + v[i];
     *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n) = pack8(v);
   } else {  // LIA_EPI_QKV
-    const int which = n / p.hq;
+    const int which = (n >= p.hq) + (n >= 2 * p.hq);   // n < 3 hq: no division (this runs once per row and 8 columns)
     const int c = n - which * p.hq;
     if (which == 0) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = v[i] * p.q_scale;
       *reinterpret_cast<uint4*>(p.q_out + (size_t)m * p.hq + c) = pack8(v);
     } else {
-      const int bb = m / p.S;
-      const int ss = m - bb * p.S;
+      int bb = m, ss = 0;                              // decode appends one position per sequence
+      if (p.S != 1) {
+        bb = m / p.S;
+        ss = m - bb * p.S;
+      }
       bf16* cache = (which == 1) ? p.k_cache : p.v_cache;
       const size_t row = (size_t)(p.pos0 + ss) * p.cache_batch + p.b0 + bb;
       *reinterpret_cast<uint4*>(cache + row * p.hq + c) = pack8(v);
@@ -250,11 +253,20 @@ __device__ __noinline__ void tp_spin(const int* flag, int epoch, int* err) {
   }
 }
 
+// optional per-CTA timeline (LIA_GEMM_TRACE=1): 16 globaltimer stamps per CTA (<= 512 CTAs) in mapped host memory
+__device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
+  if (trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+    trace[blockIdx.x * 16 + i] = t;
+  }
+}
+
 // Fused all-reduce, decode shapes, world >= 4: second half of the exchange (see the call site).  Kept out of line so
 // that the plain projections -- which share this kernel image -- pay neither its registers nor its instruction bytes.
 template <int BN>
 __device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* rb, int epoch, int parity, int* tp_err, int ta,
-                                              int m0, int n_col, int rows) {
+                                              int m0, int n_col, int rows, unsigned long long* trace = nullptr) {
   constexpr int ITERS = BN / 8;
   const TpDev& tp = p.tp;
   // ---- two-shot (world >= 4).  Ownership is per (row group, tile): the 8 values of row m = m0 + 8*it of
@@ -278,11 +290,19 @@ __device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* r
     }
     return false;
   };
+  unsigned mine = 0;                             // bit it: row group it of this tile is reduced here ((it + ta) % world == rank)
+  {
+    int o = ta % tp.world;
+    for (int it = 0; it < ITERS; ++it) {
+      if (o == tp.rank) mine |= 1u << it;
+      o = o + 1 == tp.world ? 0 : o + 1;
+    }
+  }
 #pragma unroll 1
   for (int it = 0; it < ITERS; ++it) {           // rows this rank reduces
     const int m = m0 + it * 8;
     if (m >= rows) break;
-    if ((it + ta) % tp.world != tp.rank) continue;
+    if (!((mine >> it) & 1u)) continue;
     const uint4 rsel = ldg_act(p.residual + (size_t)m * p.N + n_col);   // in flight while the partials are polled
     const uint4* q0 = rb + (((size_t)m * p.N + n_col) >> 2);
     const size_t src_stride = ((size_t)BN * p.N) >> 2;
@@ -336,6 +356,7 @@ __device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* r
     }
     *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = o;
   }
+  if (threadIdx.x == EPI_WARP0 * 32) stamp(trace, 10);
   constexpr int RG = ITERS < 4 ? ITERS : 4;      // rows other ranks reduce: their finals, RG rows in flight
 #pragma unroll 1
   for (int it0 = 0; it0 < ITERS; it0 += RG) {
@@ -346,7 +367,7 @@ __device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* r
 #pragma unroll
       for (int j = 0; j < RG; ++j) {
         const int m = m0 + (it0 + j) * 8;
-        if (m < rows && (it0 + j + ta) % tp.world != tp.rank) {
+        if (m < rows && !((mine >> (it0 + j)) & 1u)) {
           const uint4* q = rb + final_base + (((size_t)m * p.N + n_col) >> 2);
           lo[j] = ld_volatile_v4(q);
           hi[j] = ld_volatile_v4(q + 1);
@@ -358,20 +379,12 @@ __device__ __noinline__ void tp_two_shot_rows(const EpiParams& p, const uint4* r
 #pragma unroll
     for (int j = 0; j < RG; ++j) {
       const int m = m0 + (it0 + j) * 8;
-      if (m < rows && (it0 + j + ta) % tp.world != tp.rank)
+      if (m < rows && !((mine >> (it0 + j)) & 1u))
         *reinterpret_cast<uint4*>(p.out + (size_t)m * p.N + n_col) = make_uint4(lo[j].x, lo[j].z, hi[j].x, hi[j].z);
     }
   }
 }
 
-// optional per-CTA timeline (LIA_GEMM_TRACE=1): 16 globaltimer stamps per CTA (<= 512 CTAs) in mapped host memory
-__device__ __forceinline__ void stamp(unsigned long long* trace, int i) {
-  if (trace != nullptr) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
-    trace[blockIdx.x * 16 + i] = t;
-  }
-}
 
 
 // ------------------------------------------------------------------ SWAP-mode (decode, M <= 128) epilogue of one work item
@@ -413,6 +426,10 @@ __device__ __forceinline__ void swap_epilogue_tile(const EpiParams& p, const Swa
   const bool full = (w.kb0 == 0 && w.kb1 == k_blocks);
   const bool owner = (w.kb0 == 0);                   // first k-piece: this CTA finishes the tile
   const bool two_shot = tp_on && (tp.opts & 128);    // fused all-reduce, world >= 4 (see the reduce side below)
+  // two-shot: row group `it` (rows m0 + 8 it) of tile ta is reduced by rank (it + ta) % world.  Tracked incrementally as the
+  // row groups are walked: a run-time modulo is ~30 dependent instructions, this code runs on one warp per scheduler with
+  // nothing to hide them behind, and one modulo per row group and destination cost ~5 us per exchange (ncu source view)
+  int own_rank = two_shot ? w.ta % tp.world : 0;
   float* slot = ws + (size_t)cx.cta * (BN * TILE_A);
   constexpr int CH = BN >= 32 ? 32 : 16;
 #pragma unroll 1
@@ -517,16 +534,25 @@ __device__ __forceinline__ void swap_epilogue_tile(const EpiParams& p, const Swa
               const uint4 lo = make_uint4(o.x, (uint32_t)epoch, o.y, (uint32_t)epoch);
               const uint4 hi = make_uint4(o.z, (uint32_t)epoch, o.w, (uint32_t)epoch);
               const size_t idx = (((size_t)tp.rank * BN + m) * p.N + n_col) >> 2;   // uint4 index: 2 per 8 values
-              for (int r2 = 0; r2 < tp.world; ++r2) {
-                if ((tp.opts & 8) && r2 != tp.rank) continue;   // timing probe only: no remote stores
-                if (two_shot && r2 != (it0 + j + w.ta) % tp.world) continue;   // two-shot: only the row's reducing rank
-                uint4* dst = reinterpret_cast<uint4*>(tp.recv(r2, parity)) + idx;
-                st_volatile_v4(dst, lo);
-                st_volatile_v4(dst + 1, hi);
+              if (two_shot) {                                   // two-shot: only to the row group's reducing rank
+                if (!(tp.opts & 8) || own_rank == tp.rank) {    // (bit 3: timing probe only, no remote stores)
+                  uint4* dst = reinterpret_cast<uint4*>(tp.recv(own_rank, parity)) + idx;
+                  st_volatile_v4(dst, lo);
+                  st_volatile_v4(dst + 1, hi);
+                }
+              } else {
+                for (int r2 = 0; r2 < tp.world; ++r2) {
+                  if ((tp.opts & 8) && r2 != tp.rank) continue;
+                  uint4* dst = reinterpret_cast<uint4*>(tp.recv(r2, parity)) + idx;
+                  st_volatile_v4(dst, lo);
+                  st_volatile_v4(dst + 1, hi);
+                }
               }
             }
           }
+          if (two_shot) own_rank = own_rank + 1 == tp.world ? 0 : own_rank + 1;
         }
+        if (et == 0 && it0 == 0) stamp(cx.trace, 9);
       }
     }
     if (tp_on) {
@@ -613,7 +639,7 @@ __device__ __forceinline__ void swap_epilogue_tile(const EpiParams& p, const Swa
             }
           }
         } else {
-          tp_two_shot_rows<BN>(p, rb, epoch, parity, tp_err, w.ta, m0, n_col, rows);
+          tp_two_shot_rows<BN>(p, rb, epoch, parity, tp_err, w.ta, m0, n_col, rows, cx.trace);
         }
       }
       if (et == 0) stamp(cx.trace, 11);
