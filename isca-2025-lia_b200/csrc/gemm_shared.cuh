@@ -460,7 +460,10 @@ __device__ __forceinline__ void swap_epilogue_tile(const EpiParams& p, const Swa
     const unsigned tile_end = (unsigned)(w.ta + 1) * (unsigned)k_blocks;
     int last_c = cx.cta;
     if (!full) {
-      while (last_c + 1 < cx.ncta && total * (unsigned)(last_c + 1) / (unsigned)cx.ncta < tile_end) ++last_c;
+      // the last CTA whose span starts inside this tile: start(c) = total * c / ncta < tile_end  <=>  c <= (tile_end * ncta - 1) / total
+      // (one division instead of one per contributor: a tile of a small GEMM is split over up to ~8 CTAs)
+      last_c = min(cx.ncta - 1, (int)((tile_end * (unsigned)cx.ncta - 1u) / total));
+      last_c = max(last_c, cx.cta);
       if (et == 0) {
         for (int c = cx.cta + 1; c <= last_c; ++c)
           while (ld_acquire_gpu(flags + c) == 0) {
