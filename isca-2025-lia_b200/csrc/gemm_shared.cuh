@@ -464,11 +464,11 @@ __device__ __forceinline__ void swap_epilogue_tile(const EpiParams& p, const Swa
       // (one division instead of one per contributor: a tile of a small GEMM is split over up to ~8 CTAs)
       last_c = min(cx.ncta - 1, (int)((tile_end * (unsigned)cx.ncta - 1u) / total));
       last_c = max(last_c, cx.cta);
-      if (et == 0) {
-        for (int c = cx.cta + 1; c <= last_c; ++c)
-          while (ld_acquire_gpu(flags + c) == 0) {
-          }
-      }
+      // one thread per contributor polls its flag (acquire), the CTA barrier below hands what they acquired to everyone:
+      // one thread polling them one after the other paid an L2 round trip per contributor even when all were long set
+      for (int c = cx.cta + 1 + et; c <= last_c; c += 128)
+        while (ld_acquire_gpu(flags + c) == 0) {
+        }
     }
     epi_bar_sync();
     if (et == 0) stamp(cx.trace, 6);
