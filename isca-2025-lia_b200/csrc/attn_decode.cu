@@ -165,7 +165,16 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, bf16* _
 
 int pick_splits(int B, int H, int T) {
   int splits = (T + MAX_CHUNK - 1) / MAX_CHUNK;
-  const int want = (2 * lia_sm_count() + B * H - 1) / (B * H);   // aim for >= 2 CTAs per SM
+  // CTAs per SM to aim for.  6: a tensor-parallel rank keeps only H / world heads, and at B * H = 448 (OPT-30B, TP8) one CTA
+  // per (b, h) left 3 latency-bound CTAs per SM -- 24 us for 9.5 us of K/V bytes; two key ranges per (b, h) took a 16-layer
+  // stack at TP8 shapes from 152.5 to 140.0 us per layer (profiles/README.md).  Unsharded shapes (B * H >= 888) keep one
+  // CTA per (b, h) and the reference's per-element rounding of p.  LIA_ATTN_CTAS_PER_SM overrides (A/B runs).
+  static int per_sm = 0;
+  if (per_sm == 0) {
+    const char* e = getenv("LIA_ATTN_CTAS_PER_SM");
+    per_sm = (e && atoi(e) > 0) ? atoi(e) : 6;
+  }
+  const int want = (per_sm * lia_sm_count() + B * H - 1) / (B * H);
   const int cap = T / 128 > 1 ? T / 128 : 1;                     // keep >= 128 keys per CTA
   int s = want < cap ? want : cap;
   if (s > 32) s = 32;
