@@ -103,7 +103,8 @@ int lia_attn_prefill_bf16(const void* q, const void* k_cache, const void* v_cach
 /* Decode attention: one query token per sequence over T cached positions (the new token's
  * K/V row already written), NO mask (A:500).  Flash-decoding: `splits` > 1 partitions T over
  * CTAs and combines through `workspace` (lia_attn_decode_workspace_bytes()); splits == 0 lets
- * the library choose.  q [B,H,d], out [B,H*d]. */
+ * the library choose (aiming for 2 CTAs per SM), splits == -n lets it choose aiming for n CTAs
+ * per SM (a tensor-parallel rank that keeps few heads).  q [B,H,d], out [B,H*d]. */
 size_t lia_attn_decode_workspace_bytes(int B, int H, int d, int max_splits);
 int lia_attn_decode_bf16(const void* q, const void* k_cache, const void* v_cache, void* out, int B, int H, int T,
                          int d, int cache_batch, int b0, int splits, void* workspace, size_t workspace_bytes,

@@ -163,16 +163,20 @@ __global__ void attn_decode_combine_kernel(const float* __restrict__ ws, bf16* _
   out[(size_t)bh * D + e] = __float2bfloat16_rn(o / L);
 }
 
-int pick_splits(int B, int H, int T) {
+// CTAs per SM the split choice aims for.  Default 2: the unsharded shapes (B * H in the thousands) keep one CTA per (b, h)
+// and with it the reference's per-element rounding of p.  A caller whose rank keeps only H / world heads asks for more
+// (`splits` = -6 from the tensor-parallel model): at B * H = 448 (OPT-30B, TP8) one CTA per (b, h) left 3 latency-bound CTAs
+// per SM -- 24 us for 9.5 us of K/V bytes -- and two key ranges per (b, h) took a 16-layer stack at TP8 shapes from 152.5 to
+// 140.0 us per layer (profiles/README.md).  LIA_ATTN_CTAS_PER_SM overrides the default of the automatic choice (A/B runs).
+int pick_splits(int B, int H, int T, int per_sm) {
   int splits = (T + MAX_CHUNK - 1) / MAX_CHUNK;
-  // CTAs per SM to aim for.  6: a tensor-parallel rank keeps only H / world heads, and at B * H = 448 (OPT-30B, TP8) one CTA
-  // per (b, h) left 3 latency-bound CTAs per SM -- 24 us for 9.5 us of K/V bytes; two key ranges per (b, h) took a 16-layer
-  // stack at TP8 shapes from 152.5 to 140.0 us per layer (profiles/README.md).  Unsharded shapes (B * H >= 888) keep one
-  // CTA per (b, h) and the reference's per-element rounding of p.  LIA_ATTN_CTAS_PER_SM overrides (A/B runs).
-  static int per_sm = 0;
-  if (per_sm == 0) {
-    const char* e = getenv("LIA_ATTN_CTAS_PER_SM");
-    per_sm = (e && atoi(e) > 0) ? atoi(e) : 6;
+  if (per_sm <= 0) {
+    static int dflt = 0;
+    if (dflt == 0) {
+      const char* e = getenv("LIA_ATTN_CTAS_PER_SM");
+      dflt = (e && atoi(e) > 0) ? atoi(e) : 2;
+    }
+    per_sm = dflt;
   }
   const int want = (per_sm * lia_sm_count() + B * H - 1) / (B * H);
   const int cap = T / 128 > 1 ? T / 128 : 1;                     // keep >= 128 keys per CTA
@@ -197,7 +201,7 @@ extern "C" int lia_attn_decode_bf16(const void* q, const void* k_cache, const vo
   LIA_CHECK_ARG(d == 64 || d == 128, "lia_attn_decode_bf16: head_dim must be 64 or 128 (got %d)", d);
   LIA_CHECK_ARG(B > 0 && H > 0 && T > 0, "lia_attn_decode_bf16: B,H,T must be positive");
   LIA_CHECK_ARG(b0 >= 0 && b0 + B <= cache_batch, "lia_attn_decode_bf16: batch window [%d,%d) outside cache batch %d", b0, b0 + B, cache_batch);
-  if (splits <= 0) splits = pick_splits(B, H, T);
+  if (splits <= 0) splits = pick_splits(B, H, T, -splits);   // 0: automatic; -n: automatic, aiming for n CTAs per SM
   if (splits > 1 && (workspace == nullptr || workspace_bytes < (size_t)B * H * splits * (d + 2) * sizeof(float))) {
     splits = (T + MAX_CHUNK - 1) / MAX_CHUNK;   // fall back to the fewest splits that fit shared memory
     LIA_CHECK_ARG(splits == 1, "lia_attn_decode_bf16: T=%d needs a workspace of lia_attn_decode_workspace_bytes()", T);

@@ -452,7 +452,8 @@ class OPTDecoder:
         if S != 1:
             self.k.attn_prefill(q, kc, vc, nb, S, b0, out=ctx)                                           # attentions.py:493-536
         else:
-            self.k.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, workspace=ws.attn)
+            # a tensor-parallel rank keeps H / world heads: ask for more key ranges per (b, h) than the unsharded default
+            self.k.attn_decode(q, kc, vc, nb, pos0 + 1, b0, out=ctx, splits=-6 if self.layout.tp > 1 else 0, workspace=ws.attn)
         self._row_parallel(ctx, v["o_w"], v["o_b"], rows, x1, ws, big)                                # decoder.py:222-247
         if pre:
             self.k.layernorm(x1, v["ln2_w"], v["ln2_b"], LN_EPS, out=ln)                                 # decoder.py:266-272
