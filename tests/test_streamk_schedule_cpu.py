@@ -1,0 +1,88 @@
+"""The stream-K work split of the decode GEMM, restated in Python and checked for the properties the kernel relies on.
+
+Mirrors `Sched<true>` and the owner's contributor range in `swap_epilogue_tile` (isca-2025-lia_b200/csrc/gemm_shared.cuh):
+CTA c of G streams the flat (tile, k-block) range [total*c/G, total*(c+1)/G); the CTA whose piece starts a tile (kb0 == 0)
+owns it and adds the pieces of CTAs c+1 .. last_c in that fixed order, where last_c is computed in closed form
+(one division) instead of by walking the CTAs.  No GPU, no library: this is host-checkable arithmetic.
+"""
+import random
+
+import pytest
+
+
+def spans(tiles_a, k_blocks, ncta):
+    total = tiles_a * k_blocks
+    return [(total * c // ncta, total * (c + 1) // ncta) for c in range(ncta)]
+
+
+def work_items(tiles_a, k_blocks, ncta, cta):
+    """Sched<true>::next for one CTA: (ta, kb0, kb1) pieces in order."""
+    pos, end = spans(tiles_a, k_blocks, ncta)[cta]
+    out = []
+    while pos < end:
+        ta = pos // k_blocks
+        kb0 = pos - ta * k_blocks
+        left = end - pos
+        kb1 = kb0 + left if left < k_blocks - kb0 else k_blocks
+        out.append((ta, kb0, kb1))
+        pos += kb1 - kb0
+    return out
+
+
+def last_contributor_loop(tiles_a, k_blocks, ncta, cta, ta):
+    total, tile_end = tiles_a * k_blocks, (ta + 1) * k_blocks
+    last_c = cta
+    while last_c + 1 < ncta and total * (last_c + 1) // ncta < tile_end:
+        last_c += 1
+    return last_c
+
+
+def last_contributor_closed_form(tiles_a, k_blocks, ncta, cta, ta):
+    total, tile_end = tiles_a * k_blocks, (ta + 1) * k_blocks
+    return max(min(ncta - 1, (tile_end * ncta - 1) // total), cta)
+
+
+SHAPES = [
+    # tiles_a, k_blocks, CTAs: the decode projections of OPT-30B at TP1 / TP8 and the lm_head, on 148 SMs
+    (168, 112, 148), (56, 112, 148), (224, 112, 148), (56, 448, 148), (393, 112, 148),
+    (21, 112, 148), (56, 14, 148), (28, 112, 148), (56, 56, 148),
+    (1, 4, 1), (1, 600, 148), (3, 5, 2), (7, 9, 5),
+]
+
+
+@pytest.mark.parametrize("tiles_a,k_blocks,ncta", SHAPES)
+def test_every_k_block_of_every_tile_is_streamed_exactly_once(tiles_a, k_blocks, ncta):
+    seen = [[0] * k_blocks for _ in range(tiles_a)]
+    for cta in range(ncta):
+        for ta, kb0, kb1 in work_items(tiles_a, k_blocks, ncta, cta):
+            assert 0 <= kb0 < kb1 <= k_blocks
+            for kb in range(kb0, kb1):
+                seen[ta][kb] += 1
+    assert all(v == 1 for row in seen for v in row)
+
+
+@pytest.mark.parametrize("tiles_a,k_blocks,ncta", SHAPES)
+def test_owner_sums_exactly_the_other_pieces_of_its_tile_in_k_order(tiles_a, k_blocks, ncta):
+    pieces = {}                       # tile -> [(kb0, cta)]
+    for cta in range(ncta):
+        for ta, kb0, kb1 in work_items(tiles_a, k_blocks, ncta, cta):
+            pieces.setdefault(ta, []).append((kb0, cta))
+    for ta, lst in pieces.items():
+        lst.sort()
+        owner = lst[0][1]
+        assert lst[0][0] == 0
+        others = [c for _, c in lst[1:]]
+        last_c = last_contributor_closed_form(tiles_a, k_blocks, ncta, owner, ta)
+        assert others == list(range(owner + 1, last_c + 1)), (ta, owner, others, last_c)
+
+
+def test_closed_form_matches_the_walk_on_random_shapes():
+    rng = random.Random(7)
+    for _ in range(20000):
+        ncta = rng.randint(1, 160)
+        tiles_a, k_blocks = rng.randint(1, 400), rng.randint(1, 500)
+        cta = rng.randrange(ncta)
+        for ta, kb0, _ in work_items(tiles_a, k_blocks, ncta, cta):
+            if kb0 == 0:
+                assert (last_contributor_closed_form(tiles_a, k_blocks, ncta, cta, ta)
+                        == last_contributor_loop(tiles_a, k_blocks, ncta, cta, ta))
