@@ -86,3 +86,30 @@ def test_closed_form_matches_the_walk_on_random_shapes():
             if kb0 == 0:
                 assert (last_contributor_closed_form(tiles_a, k_blocks, ncta, cta, ta)
                         == last_contributor_loop(tiles_a, k_blocks, ncta, cta, ta))
+
+
+# ---- two-shot decode exchange: which rank reduces which row group (gemm_shared.cuh, swap_epilogue_tile / tp_two_shot_rows)
+def owners_incremental(ta, world, iters):
+    """The kernel's walk: one modulo per tile, then +1 with wrap per row group."""
+    own, out = ta % world, []
+    for _ in range(iters):
+        out.append(own)
+        own = 0 if own + 1 == world else own + 1
+    return out
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+@pytest.mark.parametrize("iters", [2, 4, 8, 16])
+def test_row_group_owner_walk_equals_the_modulo_it_replaced(world, iters):
+    for ta in range(0, 200):
+        want = [(it + ta) % world for it in range(iters)]
+        assert owners_incremental(ta, world, iters) == want
+        for rank in range(world):
+            mine = 0
+            for it, o in enumerate(owners_incremental(ta, world, iters)):
+                if o == rank:
+                    mine |= 1 << it
+            assert [bool((mine >> it) & 1) for it in range(iters)] == [w == rank for w in want]
+        # every row group has exactly one reducing rank, and each rank reduces its share to within one group
+        counts = [want.count(r) for r in range(world)]
+        assert sum(counts) == iters and max(counts) - min(counts) <= 1
