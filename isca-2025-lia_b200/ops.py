@@ -5,6 +5,7 @@ call into libliab200.so on ``torch.cuda.current_stream()``.  No op has a PyTorch
 fallback -- a missing library or a non-CUDA tensor raises.
 """
 import ctypes
+import os
 
 import torch
 
@@ -155,6 +156,34 @@ def attn_prefill(q, k_cache, v_cache, B, S, b0=0, out=None):
     return out
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+    key = torch.device(device).index or 0
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(key).multi_processor_count
+    return _SM_COUNT[key]
+
+
+def attn_decode_launches(B, H, T, splits, has_workspace, sms):
+    """Kernels one lia_attn_decode_bf16 call launches: 1, or 2 when it splits the keys (the split kernel and the combine).
+    Bookkeeping for ``gpu_launches`` only -- restates the choice made in csrc/attn_decode.cu (pick_splits and the fallbacks
+    after it); the kernel never sees this."""
+    fewest = (T + 4095) // 4096
+    if splits <= 0:
+        per_sm = -splits
+        if per_sm == 0:
+            env = os.environ.get("LIA_ATTN_CTAS_PER_SM", "")
+            per_sm = int(env) if env.isdigit() and int(env) > 0 else 2
+        want = (per_sm * sms + B * H - 1) // (B * H)
+        splits = max(min(want, max(T // 128, 1), 32), fewest)
+    if splits > 1 and not has_workspace:
+        splits = fewest
+    t_chunk = (T + splits - 1) // splits
+    return 2 if (T + t_chunk - 1) // t_chunk > 1 else 1
+
+
 def attn_decode(q, k_cache, v_cache, B, T, b0=0, out=None, splits=0, workspace=None):
     """One query token per sequence over T cached positions, no mask (attentions.py:395-399, 500)."""
     _req(q, "q"); _req(k_cache, "k_cache"); _req(v_cache, "v_cache")
@@ -167,7 +196,7 @@ def attn_decode(q, k_cache, v_cache, B, T, b0=0, out=None, splits=0, workspace=N
         ws_ptr, ws_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
     check(_lib.load().lia_attn_decode_bf16(_p(q), _p(k_cache), _p(v_cache), _p(_req(out, "out")), B, H, T, d, Bc, b0,
                                            splits, ws_ptr, ws_bytes, _stream()), "lia_attn_decode_bf16")
-    count_launches(2 if splits != 1 and workspace is not None else 1)
+    count_launches(attn_decode_launches(B, H, T, splits, workspace is not None, _sm_count(q.device)))
     return out
 
 

@@ -113,3 +113,22 @@ def test_row_group_owner_walk_equals_the_modulo_it_replaced(world, iters):
         # every row group has exactly one reducing rank, and each rank reduces its share to within one group
         counts = [want.count(r) for r in range(world)]
         assert sum(counts) == iters and max(counts) - min(counts) <= 1
+
+
+# ---- launch bookkeeping of the decode attention (ops.attn_decode_launches restates csrc/attn_decode.cu's split choice)
+def test_decode_attention_launch_count_follows_the_split_choice(monkeypatch):
+    import lia_b200  # noqa: F401
+    from lia_b200 import ops
+    monkeypatch.delenv("LIA_ATTN_CTAS_PER_SM", raising=False)
+    n = lambda B, H, T, splits, ws=True: ops.attn_decode_launches(B, H, T, splits, ws, 148)  # noqa: E731
+    assert n(64, 56, 288, 0) == 1          # headline, unsharded: one CTA per (b, h), the reference's rounding of p
+    assert n(64, 28, 288, -6) == 1         # TP2
+    assert n(64, 14, 288, -6) == 1         # TP4
+    assert n(64, 7, 288, 0) == 1           # TP8 shapes under the unsharded default
+    assert n(64, 7, 288, -6) == 2          # TP8 as the tensor-parallel model asks: two key ranges + the combine kernel
+    assert n(64, 7, 200, -6) == 1          # fewer than 256 keys: never split below 128 keys per CTA
+    assert n(8, 32, 300, 0) == 2           # small batch
+    assert n(8, 32, 300, 0, ws=False) == 1  # no workspace: the fewest splits that fit
+    assert n(64, 56, 288, 1) == 1 and n(64, 56, 288, 4) == 2
+    monkeypatch.setenv("LIA_ATTN_CTAS_PER_SM", "6")
+    assert n(64, 7, 288, 0) == 2
